@@ -1,0 +1,830 @@
+// C ABI of the B200-native Go2 policy hot path (declared in include/go2policy.h).
+// Host side: parse the .onnx once, upload the weights in the layouts the kernels read, own the
+// mailbox / streams / scratch, launch the sm_100a kernels.  No CPU compute path exists here.
+#include "../../include/go2policy.h"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+#include "kernels_b1.cuh"
+#include "kernels_fp32.cuh"
+#include "kernels_tc.cuh"
+#include "kernels_wide.cuh"
+#include "onnx_reader.hpp"
+
+using namespace go2p;
+
+static_assert(sizeof(go2p_raw_state) == sizeof(RawStateDev), "raw state layout");
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                              \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      return fail(GO2P_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));            \
+  } while (0)
+
+inline void cpu_relax() {
+#if defined(__x86_64__)
+  _mm_pause();
+#endif
+}
+
+constexpr int kOutSlots = 1024;
+constexpr int64_t kFp32ChunkRows = 131072;
+constexpr int64_t kHostChunkRows = 65536;
+constexpr int kPipeDepth = 3;
+
+}  // namespace
+
+struct go2p_handle {
+  go2p_config cfg{};
+  MlpModel model;
+  int device = 0, sm_count = 0, cc_major = 0, cc_minor = 0;
+  std::vector<void*> dev_owned;
+  DevModel dm{};
+  CtrlConst cc{};
+  // tensor-core path
+  bool tc_ok = false;
+  bool wide_ok = false;
+  uint16_t* d_wpack[2] = {nullptr, nullptr};   // [0] bf16, [1] fp16
+  float* d_bias_tc = nullptr;
+  int k0p = 0;
+  WideModel wide{};
+  uint32_t tc_debug = 0;
+  int tc_epw = 4;
+  // fp32 path scratch
+  float* scratch[2] = {nullptr, nullptr};
+  int64_t scratch_rows = 0;
+  // batch-1
+  B1State* d_state = nullptr;
+  MailWord* inbox = nullptr;    // host-mapped
+  MailWord* outbox = nullptr;   // host-mapped
+  int n_in_slots = 0;
+  uint32_t seq = 0;
+  bool resident = false;
+  cudaStream_t b1_stream = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  size_t b1_smem = 0;
+  bool b1_weights_in_smem = false;
+  float* bound_obs = nullptr;
+  float* bound_act = nullptr;
+  size_t n_bound_obs = 0, n_bound_act = 0;
+  go2p_b1_stats stats{0, ~0ull, 0, 0};
+  // host pipeline
+  cudaStream_t pipe_stream[kPipeDepth] = {};
+  float* pipe_in[kPipeDepth] = {};
+  float* pipe_out[kPipeDepth] = {};
+  int last_launches = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+template <class T>
+int dev_upload(go2p_handle* h, const std::vector<T>& v, T** out) {
+  void* p = nullptr;
+  CU_TRY(cudaMalloc(&p, std::max<size_t>(v.size() * sizeof(T), 16)));
+  h->dev_owned.push_back(p);
+  CU_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = static_cast<T*>(p);
+  return GO2P_OK;
+}
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+uint16_t to_bf16(float f) { return __bfloat16_as_ushort(__float2bfloat16_rn(f)); }
+uint16_t to_f16(float f) {
+  f = std::min(65504.f, std::max(-65504.f, f));
+  return __half_as_ushort(__float2half_rn(f));
+}
+
+// 16-bit K-major UMMA "interleaved" (no swizzle) layout: 8x8-element core matrices of 128 contiguous
+// bytes, K-adjacent cores contiguous (LBO = 128 B), 8-row groups Kp*16 B apart (SBO).
+void pack_umma_kmajor(const MlpLayer& L, int Np, int Kp, bool fp16, std::vector<uint16_t>& out) {
+  const size_t base = out.size();
+  out.resize(base + (size_t)Np * Kp, 0);
+  for (int n = 0; n < Np; ++n)
+    for (int k = 0; k < Kp; ++k) {
+      const float v = (n < L.out && k < L.in) ? L.weight[(size_t)n * L.in + k] : 0.f;
+      const size_t idx = ((size_t)(n / 8) * (Kp / 8) + (k / 8)) * 64 + (n % 8) * 8 + (k % 8);
+      out[base + idx] = fp16 ? to_f16(v) : to_bf16(v);
+    }
+}
+
+int upload_model(go2p_handle* h) {
+  const MlpModel& m = h->model;
+  DevModel& dm = h->dm;
+  dm.n_layers = (int)m.layers.size();
+  dm.in_dim = m.in_dim();
+  dm.out_dim = m.out_dim();
+  dm.max_width = dm.in_dim;
+  for (int l = 0; l < dm.n_layers; ++l) {
+    const MlpLayer& L = m.layers[l];
+    DevLayer& D = dm.L[l];
+    D.K = L.in; D.N = L.out;
+    D.Kp = round_up(L.in, 4);
+    D.Kp8 = round_up(L.in, 8);
+    D.Np = round_up(L.out, 128);
+    D.has_elu = L.has_elu ? 1 : 0;
+    D.alpha = L.elu_alpha;
+    dm.max_width = std::max(dm.max_width, L.out);
+    std::vector<float> rm((size_t)D.N * D.Kp, 0.f), k4((size_t)D.Kp * D.N, 0.f), kn((size_t)D.Kp8 * D.Np, 0.f), bias(D.Np, 0.f);
+    for (int o = 0; o < D.N; ++o)
+      for (int k = 0; k < D.K; ++k) {
+        const float v = L.weight[(size_t)o * L.in + k];
+        rm[(size_t)o * D.Kp + k] = v;
+        k4[((size_t)(k / 4) * D.N + o) * 4 + (k % 4)] = v;
+        kn[(size_t)k * D.Np + o] = v;
+      }
+    for (int o = 0; o < D.N; ++o) bias[o] = L.bias[o];
+    float *drm, *dk4, *dkn, *db;
+    int rc;
+    if ((rc = dev_upload(h, rm, &drm)) || (rc = dev_upload(h, k4, &dk4)) || (rc = dev_upload(h, kn, &dkn)) ||
+        (rc = dev_upload(h, bias, &db)))
+      return rc;
+    D.w_rm = drm; D.w_k4 = dk4; D.w_kn = dkn; D.bias = db;
+  }
+  // controller constants
+  for (int i = 0; i < kDof; ++i) h->cc.q0[i] = h->cfg.q0[i];
+  h->cc.action_scale = h->cfg.action_scale;
+  h->cc.action_limit = h->cfg.action_limit;
+  h->cc.kp_deadman = h->cfg.kp_deadman;
+  h->cc.foot_threshold = h->cfg.foot_threshold;
+  h->cc.H = h->cfg.history;
+
+  // ---- tensor-core packing (narrow family: every hidden width 128, in <= 128, out <= 16)
+  bool narrow = dm.n_layers >= 2 && dm.in_dim <= 128 && dm.out_dim <= kTcOutPad;
+  for (int l = 0; l + 1 < dm.n_layers; ++l) narrow = narrow && (m.layers[l].out == kTcHidden);
+  if (narrow) {
+    h->k0p = round_up(dm.in_dim, 16);
+    std::vector<uint16_t> wb, wf;
+    std::vector<float> bias((size_t)dm.n_layers * 128, 0.f);
+    for (int l = 0; l < dm.n_layers; ++l) {
+      const int Kp = l == 0 ? h->k0p : kTcHidden;
+      const int Np = l == dm.n_layers - 1 ? kTcOutPad : kTcHidden;
+      pack_umma_kmajor(m.layers[l], Np, Kp, false, wb);
+      pack_umma_kmajor(m.layers[l], Np, Kp, true, wf);
+      for (int o = 0; o < m.layers[l].out; ++o) bias[(size_t)l * 128 + o] = m.layers[l].bias[o];
+    }
+    TcArgs probe{};
+    probe.n_layers = dm.n_layers; probe.in_dim = dm.in_dim; probe.k0p = h->k0p;
+    if (tc_smem_bytes(probe) <= 227 * 1024) {
+      int rc;
+      if ((rc = dev_upload(h, wb, &h->d_wpack[0])) || (rc = dev_upload(h, wf, &h->d_wpack[1])) ||
+          (rc = dev_upload(h, bias, &h->d_bias_tc)))
+        return rc;
+      h->tc_ok = true;
+    }
+  }
+  if (!h->tc_ok) {
+    int rc = wide_prepare(m, h->dev_owned, &h->wide, g_err);
+    if (rc == 0) h->wide_ok = true;
+    else if (rc > 0) return rc;   // CUDA failure; rc < 0 means "shape not served"
+  }
+  return GO2P_OK;
+}
+
+size_t b1_smem_bytes(const go2p_handle* h, bool resident, bool* weights_fit) {
+  const int XW = b1_xw(std::max(h->dm.max_width, h->n_in_slots));
+  size_t bytes = (size_t)(2 * XW + kB1Threads + 64) * 4;
+  *weights_fit = false;
+  if (resident) {
+    bytes += sizeof(B1State);
+    size_t w = 0;
+    for (int l = 0; l < h->dm.n_layers; ++l) w += (size_t)h->dm.L[l].Kp * h->dm.L[l].N + round_up(h->dm.L[l].N, 4);
+    if (bytes + w * 4 <= 227 * 1024) { bytes += w * 4; *weights_fit = true; }
+  }
+  return bytes;
+}
+
+B1Args make_b1_args(const go2p_handle* h, bool weights_in_smem) {
+  B1Args a{};
+  a.model = h->dm;
+  a.model.max_width = std::max(h->dm.max_width, h->n_in_slots);
+  a.cc = h->cc;
+  a.gstate = h->d_state;
+  a.inbox = h->inbox;
+  a.outbox = h->outbox;
+  a.n_in_slots = h->n_in_slots;
+  a.weights_in_smem = weights_in_smem ? 1 : 0;
+  return a;
+}
+
+void mail_send(go2p_handle* h, uint32_t type, const uint32_t* words, int n, uint32_t* tag_out) {
+  const uint32_t seq = ++h->seq;
+  const uint32_t tag = make_tag(seq, type);
+  volatile uint64_t* slots = reinterpret_cast<volatile uint64_t*>(h->inbox);
+  for (int i = 0; i < h->n_in_slots; ++i) slots[i] = ((uint64_t)tag << 32) | (uint64_t)(i < n ? words[i] : 0u);
+  *tag_out = tag;
+}
+
+int mail_wait(go2p_handle* h, uint32_t tag, int n_words) {
+  const volatile uint64_t* slots = reinterpret_cast<const volatile uint64_t*>(h->outbox);
+  const auto t0 = std::chrono::steady_clock::now();
+  uint64_t spins = 0;
+  for (int i = n_words - 1; i >= 0; --i) {
+    while ((uint32_t)(slots[i] >> 32) != tag) {
+      cpu_relax();
+      if ((++spins & 0xFFFF) == 0) {
+        const auto dt = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
+        if (dt > h->cfg.timeout_ms) {
+          cudaError_t e = cudaPeekAtLastError();
+          if (e == cudaSuccess && h->b1_stream) e = cudaStreamQuery(h->b1_stream);
+          return fail(GO2P_ERR_TIMEOUT, std::string("batch-1 kernel did not answer within timeout (cuda: ") +
+                                            cudaGetErrorString(e == cudaErrorNotReady ? cudaSuccess : e) + ")");
+        }
+      }
+    }
+  }
+  return GO2P_OK;
+}
+
+int b1_dispatch(go2p_handle* h) {
+  // called after mail_send: make sure some kernel will consume the message
+  if (h->cfg.b1_mode == GO2P_B1_PERSISTENT) {
+    if (!h->resident) return go2p_persistent_start(h);
+    return GO2P_OK;
+  }
+  if (h->cfg.b1_mode == GO2P_B1_GRAPH) {
+    if (!h->graph_exec) {
+      bool fit;
+      const size_t smem = b1_smem_bytes(h, false, &fit);
+      CU_TRY(cudaFuncSetAttribute(b1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      B1Args a = make_b1_args(h, false);
+      CU_TRY(cudaStreamBeginCapture(h->b1_stream, cudaStreamCaptureModeThreadLocal));
+      b1_kernel<false><<<1, kB1Threads, smem, h->b1_stream>>>(a);
+      CU_TRY(cudaStreamEndCapture(h->b1_stream, &h->graph));
+      CU_TRY(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
+    }
+    CU_TRY(cudaGraphLaunch(h->graph_exec, h->b1_stream));
+    return GO2P_OK;
+  }
+  bool fit;
+  const size_t smem = b1_smem_bytes(h, false, &fit);
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    CU_TRY(cudaFuncSetAttribute(b1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  B1Args a = make_b1_args(h, false);
+  b1_kernel<false><<<1, kB1Threads, smem, h->b1_stream>>>(a);
+  CU_TRY(cudaGetLastError());
+  return GO2P_OK;
+}
+
+void stats_add(go2p_handle* h, uint64_t ns) {
+  h->stats.steps++;
+  h->stats.device_ns_sum += ns;
+  h->stats.device_ns_min = std::min(h->stats.device_ns_min, ns);
+  h->stats.device_ns_max = std::max(h->stats.device_ns_max, ns);
+}
+
+int simple_message(go2p_handle* h, uint32_t type, const uint32_t* words, int n) {
+  DeviceGuard g(h->device);
+  uint32_t tag;
+  mail_send(h, type, words, n, &tag);
+  int rc = b1_dispatch(h);
+  if (rc) return rc;
+  return mail_wait(h, tag, 1);
+}
+
+int ensure_scratch(go2p_handle* h, int64_t rows) {
+  if (h->scratch_rows >= rows) return GO2P_OK;
+  for (int i = 0; i < 2; ++i) {
+    if (h->scratch[i]) cudaFree(h->scratch[i]);
+    h->scratch[i] = nullptr;
+  }
+  const size_t bytes = (size_t)rows * h->dm.max_width * sizeof(float);
+  CU_TRY(cudaMalloc((void**)&h->scratch[0], bytes));
+  CU_TRY(cudaMalloc((void**)&h->scratch[1], bytes));
+  h->scratch_rows = rows;
+  return GO2P_OK;
+}
+
+int launch_fp32(go2p_handle* h, const float* d_obs, const int32_t* d_button0, float* d_act, double* d_qdes,
+                int64_t B, uint32_t flags, cudaStream_t st) {
+  const DevModel& dm = h->dm;
+  const int64_t chunk = std::min<int64_t>(B, kFp32ChunkRows);
+  int rc = ensure_scratch(h, chunk);
+  if (rc) return rc;
+  for (int64_t r0 = 0; r0 < B; r0 += chunk) {
+    const int64_t rows = std::min(chunk, B - r0);
+    const float* in = d_obs + r0 * dm.in_dim;
+    int lda = dm.in_dim;
+    for (int l = 0; l < dm.n_layers; ++l) {
+      const DevLayer& L = dm.L[l];
+      const bool last = l == dm.n_layers - 1;
+      float* out = last ? d_act + r0 * dm.out_dim : h->scratch[l & 1];
+      const int ldc = L.N;
+      if (last && L.N <= 32) {
+        const size_t smem = ((size_t)kSoRows * (L.K | 1) + (size_t)L.N * L.Kp) * sizeof(float);
+        CU_TRY(cudaFuncSetAttribute(small_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        small_out_kernel<<<(unsigned)((rows + kSoRows - 1) / kSoRows), kSoRows, smem, st>>>(
+            in, lda, L.w_rm, L.Kp, L.bias, out, ldc, rows, L.K, L.N, L.has_elu, L.alpha, flags,
+            d_button0 ? d_button0 + r0 : nullptr, d_qdes ? d_qdes + r0 * kDof : nullptr, h->cc);
+        h->last_launches++;
+      } else {
+        dim3 grid((unsigned)((rows + kSgBM - 1) / kSgBM), (unsigned)(L.Np / kSgBN));
+        sgemm_bias_act_kernel<<<grid, kSgThreads, 0, st>>>(in, lda, L.w_kn, L.Np, L.bias, out, ldc, (int)rows, L.K, L.N,
+                                                          L.has_elu, L.alpha);
+        h->last_launches++;
+        if (last && flags) {
+          const long long total = rows * (long long)dm.out_dim;
+          post_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, total, dm.out_dim, flags,
+                                                                      d_button0 ? d_button0 + r0 : nullptr,
+                                                                      d_qdes ? d_qdes + r0 * kDof : nullptr, h->cc);
+          h->last_launches++;
+        }
+      }
+      in = out;
+      lda = ldc;
+    }
+  }
+  CU_TRY(cudaGetLastError());
+  return GO2P_OK;
+}
+
+template <bool kFp16, int kEpw>
+int launch_tc_t(go2p_handle* h, const TcArgs& a, cudaStream_t st) {
+  const size_t smem = tc_smem_bytes(a);
+  static thread_local size_t set_for = 0;
+  if (set_for != smem) {
+    CU_TRY(cudaFuncSetAttribute(tc_mlp_kernel<kFp16, kEpw>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    set_for = smem;
+  }
+  const long long tiles = (a.B + kTcTileM - 1) / kTcTileM;
+  int grid = (int)std::min<long long>(tiles, h->sm_count - (h->resident ? 1 : 0));
+  tc_mlp_kernel<kFp16, kEpw><<<grid, (kTcCtrlWarps + 2 * kEpw) * 32, smem, st>>>(a);
+  h->last_launches++;
+  CU_TRY(cudaGetLastError());
+  return GO2P_OK;
+}
+
+int launch_tc(go2p_handle* h, const float* d_obs, const int32_t* d_button0, float* d_act, double* d_qdes, int64_t B,
+              bool fp16, uint32_t flags, cudaStream_t st) {
+  if ((reinterpret_cast<uintptr_t>(d_obs) & 15) || (reinterpret_cast<uintptr_t>(d_act) & 15) ||
+      (d_qdes && (reinterpret_cast<uintptr_t>(d_qdes) & 15)))
+    return fail(GO2P_ERR_INVALID, "tensor-core path needs 16-byte aligned obs/act/qdes device pointers");
+  TcArgs a{};
+  a.obs = d_obs; a.act = d_act; a.button0 = d_button0; a.qdes = d_qdes; a.B = B;
+  a.wpack = h->d_wpack[fp16 ? 1 : 0];
+  a.bias = h->d_bias_tc;
+  a.n_layers = h->dm.n_layers; a.in_dim = h->dm.in_dim; a.k0p = h->k0p; a.out_dim = h->dm.out_dim;
+  for (int l = 0; l < h->dm.n_layers; ++l) { a.has_elu[l] = h->dm.L[l].has_elu; a.alpha[l] = h->dm.L[l].alpha; }
+  a.flags = flags;
+  a.action_limit = h->cc.action_limit;
+  a.action_scale = h->cc.action_scale;
+  for (int i = 0; i < kDof; ++i) a.q0[i] = h->cc.q0[i];
+  if (h->tc_epw == 8) return fp16 ? launch_tc_t<true, 8>(h, a, st) : launch_tc_t<false, 8>(h, a, st);
+  return fp16 ? launch_tc_t<true, 4>(h, a, st) : launch_tc_t<false, 4>(h, a, st);
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int go2p_abi_version(void) { return GO2P_ABI_VERSION; }
+const char* go2p_last_error(void) { return g_err.c_str(); }
+
+void go2p_config_default(go2p_config* c) {
+  if (!c) return;
+  std::memset(c, 0, sizeof(*c));
+  c->struct_size = sizeof(go2p_config);
+  c->device = 0;
+  c->b1_mode = GO2P_B1_PERSISTENT;
+  if (const char* e = std::getenv("GO2P_B1_MODE")) {
+    if (!std::strcmp(e, "graph")) c->b1_mode = GO2P_B1_GRAPH;
+    else if (!std::strcmp(e, "launch")) c->b1_mode = GO2P_B1_LAUNCH;
+  }
+  c->history = 2;                                   // controller.hpp:15
+  c->action_limit = 1000.0f;                        // controller.hpp:16
+  c->action_scale = 0.25;                           // controller.cpp:244
+  const double q0[12] = {0.1, -0.1, 0.1, -0.1, 0.8, 0.8, 1.0, 1.0, -1.5, -1.5, -1.5, -1.5};   // controller.hpp:165
+  std::memcpy(c->q0, q0, sizeof(q0));
+  c->foot_threshold = 22;                           // controller.hpp:100-103
+  c->kp = 28.0f; c->kd = 0.5f;                      // controller.hpp:119-120
+  c->kp_deadman = 5.0f;                             // controller.cpp:246
+  c->log_level = 2;
+  c->timeout_ms = 2000;
+}
+
+int go2p_create(const char* onnx_path, const go2p_config* cfg_in, go2p_handle** out) {
+  if (!onnx_path || !out) return fail(GO2P_ERR_INVALID, "go2p_create: null argument");
+  *out = nullptr;
+  go2p_config cfg;
+  go2p_config_default(&cfg);
+  if (cfg_in) {
+    if (cfg_in->struct_size != sizeof(go2p_config)) return fail(GO2P_ERR_INVALID, "go2p_config.struct_size mismatch (ABI)");
+    cfg = *cfg_in;
+  }
+  if (cfg.history < 1 || cfg.history > GO2P_MAX_HISTORY) return fail(GO2P_ERR_INVALID, "history must be in [1,8]");
+
+  MlpModel model;
+  try {
+    model = load_onnx_mlp(onnx_path);
+  } catch (const std::exception& e) {
+    const std::string w = e.what();
+    return fail(w.rfind("io:", 0) == 0 ? GO2P_ERR_IO : GO2P_ERR_MODEL, w);
+  }
+  if ((int)model.layers.size() > kMaxLayers) return fail(GO2P_ERR_UNSUPPORTED, "more than 8 Gemm layers");
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(GO2P_ERR_NO_DEVICE, "no CUDA device visible: this library has no CPU fallback");
+  }
+  if (cfg.device < 0 || cfg.device >= ndev) return fail(GO2P_ERR_INVALID, "device ordinal out of range");
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, cfg.device));
+  if (prop.major != 10)
+    return fail(GO2P_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                                        std::to_string(prop.minor) + "; the kernels are built for sm_100a only (no fallback)");
+
+  auto* h = new go2p_handle();
+  h->cfg = cfg;
+  h->model = std::move(model);
+  h->device = cfg.device;
+  h->sm_count = prop.multiProcessorCount;
+  h->cc_major = prop.major;
+  h->cc_minor = prop.minor;
+  if (const char* e = std::getenv("GO2P_TC_DEBUG")) h->tc_debug = (uint32_t)std::strtoul(e, nullptr, 0);
+  if (const char* e = std::getenv("GO2P_TC_EPW")) h->tc_epw = std::atoi(e) == 8 ? 8 : 4;
+  DeviceGuard g(h->device);
+  int rc = upload_model(h);
+  if (rc == GO2P_OK) {
+    h->n_in_slots = round_up(std::max(h->dm.in_dim, kRawWords), 32);
+    if (h->n_in_slots > kB1Threads) rc = fail(GO2P_ERR_UNSUPPORTED, "batch-1 path supports in_dim <= 512");
+  }
+  auto cuda_part = [&]() -> int {
+    CU_TRY(cudaStreamCreateWithFlags(&h->b1_stream, cudaStreamNonBlocking));
+    CU_TRY(cudaHostAlloc((void**)&h->inbox, sizeof(MailWord) * kB1Threads, cudaHostAllocMapped));
+    CU_TRY(cudaHostAlloc((void**)&h->outbox, sizeof(MailWord) * kOutSlots, cudaHostAllocMapped));
+    std::memset(h->inbox, 0, sizeof(MailWord) * kB1Threads);
+    std::memset(h->outbox, 0, sizeof(MailWord) * kOutSlots);
+    CU_TRY(cudaMalloc((void**)&h->d_state, sizeof(B1State)));
+    B1State init{};
+    init.kp = h->cfg.kp;
+    init.kd = h->cfg.kd;
+    CU_TRY(cudaMemcpy(h->d_state, &init, sizeof(init), cudaMemcpyHostToDevice));
+    for (int i = 0; i < kPipeDepth; ++i) CU_TRY(cudaStreamCreateWithFlags(&h->pipe_stream[i], cudaStreamNonBlocking));
+    return GO2P_OK;
+  };
+  if (rc == GO2P_OK) rc = cuda_part();
+  if (rc != GO2P_OK) {
+    const std::string keep = g_err;
+    go2p_destroy(h);
+    g_err = keep;
+    return rc;
+  }
+  *out = h;
+  return GO2P_OK;
+}
+
+int go2p_destroy(go2p_handle* h) {
+  if (!h) return GO2P_OK;
+  DeviceGuard g(h->device);
+  if (h->resident) go2p_persistent_stop(h);
+  if (h->b1_stream) cudaStreamSynchronize(h->b1_stream);
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  if (h->graph) cudaGraphDestroy(h->graph);
+  for (int i = 0; i < kPipeDepth; ++i) {
+    if (h->pipe_stream[i]) { cudaStreamSynchronize(h->pipe_stream[i]); cudaStreamDestroy(h->pipe_stream[i]); }
+    if (h->pipe_in[i]) cudaFree(h->pipe_in[i]);
+    if (h->pipe_out[i]) cudaFree(h->pipe_out[i]);
+  }
+  if (h->b1_stream) cudaStreamDestroy(h->b1_stream);
+  for (void* p : h->dev_owned) cudaFree(p);
+  for (int i = 0; i < 2; ++i) if (h->scratch[i]) cudaFree(h->scratch[i]);
+  if (h->d_state) cudaFree(h->d_state);
+  if (h->inbox) cudaFreeHost(h->inbox);
+  if (h->outbox) cudaFreeHost(h->outbox);
+  delete h;
+  return GO2P_OK;
+}
+
+int go2p_model_info(const go2p_handle* h, go2p_model_info_t* info) {
+  if (!h || !info) return fail(GO2P_ERR_INVALID, "go2p_model_info: null argument");
+  std::memset(info, 0, sizeof(*info));
+  info->in_dim = h->dm.in_dim;
+  info->out_dim = h->dm.out_dim;
+  info->n_layers = h->dm.n_layers;
+  info->dims[0] = h->dm.in_dim;
+  for (int l = 0; l < h->dm.n_layers; ++l) {
+    info->dims[l + 1] = h->dm.L[l].N;
+    info->has_elu[l] = h->dm.L[l].has_elu;
+    info->elu_alpha[l] = h->dm.L[l].alpha;
+  }
+  info->input_name = h->model.input_name.c_str();
+  info->output_name = h->model.output_name.c_str();
+  info->n_params = h->model.n_params();
+  info->sm_count = h->sm_count;
+  info->cc_major = h->cc_major;
+  info->cc_minor = h->cc_minor;
+  info->tensor_core_path = (h->tc_ok || h->wide_ok) ? 1 : 0;
+  return GO2P_OK;
+}
+
+// ------------------------------------------------------------------------------------- batch-1
+int go2p_persistent_start(go2p_handle* h) {
+  if (!h) return fail(GO2P_ERR_INVALID, "null handle");
+  if (h->resident) return GO2P_OK;
+  DeviceGuard g(h->device);
+  bool fit = false;
+  const size_t smem = b1_smem_bytes(h, true, &fit);
+  CU_TRY(cudaFuncSetAttribute(b1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B1Args a = make_b1_args(h, fit);
+  b1_kernel<true><<<1, kB1Threads, smem, h->b1_stream>>>(a);
+  CU_TRY(cudaGetLastError());
+  h->resident = true;
+  h->b1_smem = smem;
+  h->b1_weights_in_smem = fit;
+  return GO2P_OK;
+}
+
+int go2p_persistent_stop(go2p_handle* h) {
+  if (!h) return fail(GO2P_ERR_INVALID, "null handle");
+  if (!h->resident) return GO2P_OK;
+  DeviceGuard g(h->device);
+  uint32_t tag;
+  mail_send(h, MSG_EXIT, nullptr, 0, &tag);
+  int rc = mail_wait(h, tag, 1);
+  h->resident = false;
+  if (rc) return rc;
+  CU_TRY(cudaStreamSynchronize(h->b1_stream));
+  return GO2P_OK;
+}
+
+int go2p_bind(go2p_handle* h, float* obs, size_t n_obs, float* act, size_t n_act) {
+  if (!h || !obs || !act) return fail(GO2P_ERR_INVALID, "go2p_bind: null argument");
+  if ((int)n_obs < h->dm.in_dim || (int)n_act < h->dm.out_dim)
+    return fail(GO2P_ERR_INVALID, "go2p_bind: buffers smaller than the model's input/output dimension");
+  h->bound_obs = obs; h->n_bound_obs = n_obs;
+  h->bound_act = act; h->n_bound_act = n_act;
+  return GO2P_OK;
+}
+
+int go2p_act(go2p_handle* h) {
+  if (!h) return fail(GO2P_ERR_INVALID, "null handle");
+  if (!h->bound_obs) return fail(GO2P_ERR_STATE, "go2p_act: no buffers bound (go2p_bind)");
+  DeviceGuard g(h->device);
+  uint32_t tag;
+  mail_send(h, MSG_ACT, reinterpret_cast<const uint32_t*>(h->bound_obs), h->dm.in_dim, &tag);
+  int rc = b1_dispatch(h);
+  if (rc) return rc;
+  const int n = h->dm.out_dim;
+  rc = mail_wait(h, tag, n + 2);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) {
+    const uint32_t bits = h->outbox[i].bits;
+    std::memcpy(&h->bound_act[i], &bits, 4);
+  }
+  stats_add(h, (uint64_t)h->outbox[n].bits | ((uint64_t)h->outbox[n + 1].bits << 32));
+  return GO2P_OK;
+}
+
+int go2p_step_fused(go2p_handle* h, const go2p_raw_state* raw, go2p_step_out* out) {
+  if (!h || !raw || !out) return fail(GO2P_ERR_INVALID, "go2p_step_fused: null argument");
+  const int n_obs = GO2P_FRAME * h->cfg.history;
+  if (h->dm.in_dim != n_obs || h->dm.out_dim != GO2P_DOF)
+    return fail(GO2P_ERR_UNSUPPORTED, "fused step needs a policy with 49*history inputs and 12 outputs");
+  DeviceGuard g(h->device);
+  uint32_t w[kRawWords];
+  std::memcpy(&w[0], raw->quat, 16);
+  std::memcpy(&w[4], raw->gyro, 12);
+  std::memcpy(&w[7], raw->q, 48);
+  std::memcpy(&w[19], raw->dq, 48);
+  std::memcpy(&w[31], raw->axes, 16);
+  for (int i = 0; i < 4; ++i) w[35 + i] = (uint32_t)(int32_t)raw->foot_force[i];
+  w[39] = (uint32_t)(raw->joy_valid != 0);
+  w[40] = (uint32_t)raw->button0;
+  uint32_t tag;
+  mail_send(h, MSG_STEP, w, kRawWords, &tag);
+  int rc = b1_dispatch(h);
+  if (rc) return rc;
+  rc = mail_wait(h, tag, n_obs + 54);
+  if (rc) return rc;
+  const MailWord* ob = h->outbox;
+  auto f32 = [&](int i) { float f; const uint32_t b = ob[i].bits; std::memcpy(&f, &b, 4); return f; };
+  auto f64 = [&](int i) { double d; const uint64_t b = (uint64_t)ob[i].bits | ((uint64_t)ob[i + 1].bits << 32); std::memcpy(&d, &b, 8); return d; };
+  for (int i = 0; i < n_obs; ++i) out->observation[i] = f32(i);
+  for (int i = 0; i < 12; ++i) {
+    out->action_raw[i] = f32(n_obs + i);
+    out->action[i] = f32(n_obs + 12 + i);
+    out->q_des[i] = f64(n_obs + 24 + 2 * i);
+  }
+  out->kp = f64(n_obs + 48);
+  out->kd = f64(n_obs + 50);
+  out->device_ns = (uint64_t)ob[n_obs + 52].bits | ((uint64_t)ob[n_obs + 53].bits << 32);
+  stats_add(h, out->device_ns);
+  return GO2P_OK;
+}
+
+int go2p_reset_history(go2p_handle* h) {
+  if (!h) return fail(GO2P_ERR_INVALID, "null handle");
+  return simple_message(h, MSG_RESET, nullptr, 0);
+}
+
+int go2p_set_gains(go2p_handle* h, float kp, float kd) {
+  if (!h) return fail(GO2P_ERR_INVALID, "null handle");
+  uint32_t w[2];
+  std::memcpy(&w[0], &kp, 4);
+  std::memcpy(&w[1], &kd, 4);
+  return simple_message(h, MSG_GAINS, w, 2);
+}
+
+int go2p_b1_stats_get(go2p_handle* h, go2p_b1_stats* out, int reset) {
+  if (!h || !out) return fail(GO2P_ERR_INVALID, "null argument");
+  *out = h->stats;
+  if (out->steps == 0) out->device_ns_min = 0;
+  if (reset) h->stats = go2p_b1_stats{0, ~0ull, 0, 0};
+  return GO2P_OK;
+}
+
+// ------------------------------------------------------------------------------------- batched
+int go2p_infer_batch_ex(go2p_handle* h, const float* d_obs, const int32_t* d_button0, float* d_act, double* d_qdes,
+                        int64_t B, int precision, uint32_t flags, void* stream) {
+  if (!h || !d_obs || !d_act) return fail(GO2P_ERR_INVALID, "go2p_infer_batch: null argument");
+  if (B < 0) return fail(GO2P_ERR_INVALID, "negative batch");
+  if ((flags & GO2P_F_QDES) && (!d_qdes || h->dm.out_dim != GO2P_DOF))
+    return fail(GO2P_ERR_INVALID, "GO2P_F_QDES needs d_qdes and a 12-output policy");
+  h->last_launches = 0;
+  if (B == 0) return GO2P_OK;
+  DeviceGuard g(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (precision) {
+    case GO2P_PREC_FP32: return launch_fp32(h, d_obs, d_button0, d_act, d_qdes, B, flags, st);
+    case GO2P_PREC_BF16:
+    case GO2P_PREC_FP16:
+      if (h->tc_ok) return launch_tc(h, d_obs, d_button0, d_act, d_qdes, B, precision == GO2P_PREC_FP16, flags, st);
+      if (h->wide_ok) {
+        int rc = ensure_scratch(h, std::min<int64_t>(B, kFp32ChunkRows));
+        if (rc) return rc;
+        rc = wide_launch(h->wide, d_obs, d_button0, d_act, d_qdes, B, precision == GO2P_PREC_FP16, flags, h->cc,
+                         h->sm_count, st, &h->last_launches, g_err);
+        return rc;
+      }
+      return fail(GO2P_ERR_UNSUPPORTED, "tensor-core kernels do not serve this layer shape; use GO2P_PREC_FP32");
+    case GO2P_PREC_TF32:
+      return fail(GO2P_ERR_UNSUPPORTED,
+                  "kind::tf32 is not built: fp32 weights of the policy do not fit beside the observation ring in "
+                  "shared memory; GO2P_PREC_FP16 has the same 11-bit significand");
+    default: return fail(GO2P_ERR_INVALID, "unknown precision");
+  }
+}
+
+int go2p_infer_batch(go2p_handle* h, const float* d_obs, float* d_act, int64_t B, int precision, void* stream) {
+  return go2p_infer_batch_ex(h, d_obs, nullptr, d_act, nullptr, B, precision, 0u, stream);
+}
+
+int go2p_last_launch_count(const go2p_handle* h) { return h ? h->last_launches : 0; }
+
+int go2p_infer_batch_host(go2p_handle* h, const float* h_obs, float* h_act, int64_t B, int precision) {
+  if (!h || !h_obs || !h_act) return fail(GO2P_ERR_INVALID, "go2p_infer_batch_host: null argument");
+  if (B <= 0) return B == 0 ? GO2P_OK : fail(GO2P_ERR_INVALID, "negative batch");
+  DeviceGuard g(h->device);
+  const int in = h->dm.in_dim, out = h->dm.out_dim;
+  const int64_t chunk = std::min<int64_t>(B, kHostChunkRows);
+  for (int i = 0; i < kPipeDepth; ++i) {
+    if (!h->pipe_in[i]) {
+      CU_TRY(cudaMalloc((void**)&h->pipe_in[i], (size_t)kHostChunkRows * in * sizeof(float)));
+      CU_TRY(cudaMalloc((void**)&h->pipe_out[i], (size_t)kHostChunkRows * out * sizeof(float)));
+    }
+  }
+  int launches = 0;
+  int slot = 0;
+  for (int64_t r0 = 0; r0 < B; r0 += chunk, slot = (slot + 1) % kPipeDepth) {
+    const int64_t rows = std::min(chunk, B - r0);
+    cudaStream_t st = h->pipe_stream[slot];
+    CU_TRY(cudaMemcpyAsync(h->pipe_in[slot], h_obs + r0 * in, (size_t)rows * in * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc = go2p_infer_batch_ex(h, h->pipe_in[slot], nullptr, h->pipe_out[slot], nullptr, rows, precision, 0u, st);
+    if (rc) return rc;
+    launches += h->last_launches;
+    CU_TRY(cudaMemcpyAsync(h_act + r0 * out, h->pipe_out[slot], (size_t)rows * out * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  for (int i = 0; i < kPipeDepth; ++i) CU_TRY(cudaStreamSynchronize(h->pipe_stream[i]));
+  h->last_launches = launches;
+  return GO2P_OK;
+}
+
+int go2p_assemble_batch(go2p_handle* h, const go2p_raw_state* d_raw, const float* d_prev_action, float* d_vel_cmd,
+                        float* d_obs, int64_t B, void* stream) {
+  if (!h || !d_raw || !d_vel_cmd || !d_obs) return fail(GO2P_ERR_INVALID, "go2p_assemble_batch: null argument");
+  if (B <= 0) return B == 0 ? GO2P_OK : fail(GO2P_ERR_INVALID, "negative batch");
+  DeviceGuard g(h->device);
+  const int n_obs = kFrame * h->cc.H;
+  const int threads = round_up(n_obs, 32);
+  const unsigned grid = (unsigned)std::min<int64_t>(B, (int64_t)h->sm_count * 16);
+  assemble_batch_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const RawStateDev*>(d_raw), d_prev_action, d_vel_cmd, d_obs, B, h->cc);
+  h->last_launches = 1;
+  CU_TRY(cudaGetLastError());
+  return GO2P_OK;
+}
+
+// ------------------------------------------------------------------------------------- helpers
+int go2p_dev_alloc(go2p_handle* h, size_t bytes, void** dptr) {
+  if (!h || !dptr) return fail(GO2P_ERR_INVALID, "null argument");
+  DeviceGuard g(h->device);
+  CU_TRY(cudaMalloc(dptr, std::max<size_t>(bytes, 16)));
+  return GO2P_OK;
+}
+int go2p_dev_free(go2p_handle* h, void* dptr) {
+  if (!h) return fail(GO2P_ERR_INVALID, "null handle");
+  if (h->resident) return fail(GO2P_ERR_STATE, "cudaFree would block on the resident batch-1 kernel; stop it first");
+  DeviceGuard g(h->device);
+  CU_TRY(cudaFree(dptr));
+  return GO2P_OK;
+}
+int go2p_host_alloc(go2p_handle* h, size_t bytes, void** hptr) {
+  if (!h || !hptr) return fail(GO2P_ERR_INVALID, "null argument");
+  DeviceGuard g(h->device);
+  CU_TRY(cudaHostAlloc(hptr, std::max<size_t>(bytes, 16), cudaHostAllocDefault));
+  return GO2P_OK;
+}
+int go2p_host_free(go2p_handle* h, void* hptr) {
+  if (!h) return fail(GO2P_ERR_INVALID, "null handle");
+  if (h->resident) return fail(GO2P_ERR_STATE, "cudaFreeHost would block on the resident batch-1 kernel; stop it first");
+  DeviceGuard g(h->device);
+  CU_TRY(cudaFreeHost(hptr));
+  return GO2P_OK;
+}
+int go2p_memcpy_h2d(go2p_handle* h, void* dptr, const void* hptr, size_t bytes, void* stream) {
+  if (!h) return fail(GO2P_ERR_INVALID, "null handle");
+  DeviceGuard g(h->device);
+  CU_TRY(cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+  return GO2P_OK;
+}
+int go2p_memcpy_d2h(go2p_handle* h, void* hptr, const void* dptr, size_t bytes, void* stream) {
+  if (!h) return fail(GO2P_ERR_INVALID, "null handle");
+  DeviceGuard g(h->device);
+  CU_TRY(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+  return GO2P_OK;
+}
+int go2p_stream_sync(go2p_handle* h, void* stream) {
+  if (!h) return fail(GO2P_ERR_INVALID, "null handle");
+  DeviceGuard g(h->device);
+  CU_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return GO2P_OK;
+}
+
+int go2p_time_batch(go2p_handle* h, const float* d_obs, const int32_t* d_button0, float* d_act, double* d_qdes,
+                    int64_t B, int precision, uint32_t flags, void* stream, int iters, float* total_ms) {
+  if (!h || !total_ms || iters < 1) return fail(GO2P_ERR_INVALID, "go2p_time_batch: bad argument");
+  DeviceGuard g(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaEvent_t e0, e1;
+  CU_TRY(cudaEventCreate(&e0));
+  CU_TRY(cudaEventCreate(&e1));
+  CU_TRY(cudaEventRecord(e0, st));
+  int launches = 0;
+  for (int i = 0; i < iters; ++i) {
+    int rc = go2p_infer_batch_ex(h, d_obs, d_button0, d_act, d_qdes, B, precision, flags, stream);
+    if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+    launches += h->last_launches;
+  }
+  CU_TRY(cudaEventRecord(e1, st));
+  CU_TRY(cudaEventSynchronize(e1));
+  CU_TRY(cudaEventElapsedTime(total_ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  h->last_launches = launches;
+  return GO2P_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,55 @@
+// Device-side view of a parsed MLP policy + the controller constants, shared by all kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace go2p {
+
+constexpr int kMaxLayers = 8;
+constexpr int kDof = 12;
+constexpr int kFrame = 49;
+constexpr int kMaxHistory = 8;
+
+struct DevLayer {
+  const float* w_rm;   // [N][Kp]        row-major, Kp = K rounded up to 4 (zero padded)
+  const float* w_k4;   // [Kp/4][N][4]   k-group major: thread o reads float4 #(k4*N + o)
+  const float* w_kn;   // [Kp8][Np]      k-major (transposed), Np = N rounded up to 128, Kp8 = K rounded up to 8
+  const float* bias;   // [Np]           zero padded
+  int K, Kp, N, Np, Kp8;
+  int has_elu;
+  float alpha;
+};
+
+struct DevModel {
+  int n_layers, in_dim, out_dim, max_width;
+  DevLayer L[kMaxLayers];
+};
+
+// reference constants (controller.hpp:13-16,100-103,119-120,165; controller.cpp:244,246)
+struct CtrlConst {
+  double q0[kDof];
+  double action_scale;
+  float action_limit;
+  float kp_deadman;
+  int foot_threshold;
+  int H;
+};
+
+// std::clamp(a,-lim,lim) then a *= (button0==0)   (controller.cpp:218-223)
+// NaN passes through the clamp (no fminf/fmaxf!), the multiply keeps the sign of zero.
+__device__ __forceinline__ float clamp_mask(float a, float lim, int button0) {
+  a = (a < -lim) ? -lim : ((lim < a) ? lim : a);
+  return __fmul_rn(a, (button0 == 0) ? 1.0f : 0.0f);
+}
+
+// q_des = q0 + (double)a * scale   (controller.cpp:244) -- no contraction into an FMA
+__device__ __forceinline__ double joint_target(float a, double q0, double scale) {
+  return __dadd_rn(q0, __dmul_rn((double)a, scale));
+}
+
+// ONNX Elu-6: x < 0 ? alpha*(exp(x)-1) : x ; NaN and -0.0 pass through
+__device__ __forceinline__ float elu_exact(float v, float alpha) {
+  return (v < 0.0f) ? alpha * (expf(v) - 1.0f) : v;
+}
+
+}  // namespace go2p

@@ -1,0 +1,189 @@
+/* go2policy -- C ABI of the B200-native Go2 policy hot path.
+ *
+ * This is the drop-in boundary: everything the reference does between
+ * ONNXController::publish() gathering its inputs and handing joint targets to the
+ * robot interface, i.e.
+ *     A1-A6  observation assembly          reference: onnx_controller/src/controller.cpp:173-212
+ *     A7     ONNXActor::act()              reference: onnx_inference/src/cpp/onnx_actor.cpp:38-48
+ *                                          (Ort::Session::Run on onnx_inference/data/model.onnx)
+ *     A9     clamp + dead-man mask         reference: controller.cpp:217-223
+ *     A11    joint targets / gains         reference: controller.cpp:235-248
+ * re-implemented as hand-written sm_100a CUDA kernels.  Plain C types only -- no
+ * CUDA, torch or ONNX Runtime type crosses this boundary (streams are void*).
+ *
+ * There is NO CPU fallback: go2p_create fails (GO2P_ERR_NO_DEVICE) when no
+ * sm_100 device is present, and every compute entry point fails loudly rather than
+ * computing on the host.
+ *
+ * All functions return 0 (GO2P_OK) on success or a go2p_status error code;
+ * go2p_last_error() returns a thread-local human-readable message.
+ */
+#ifndef GO2POLICY_H
+#define GO2POLICY_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GO2P_ABI_VERSION 1
+#define GO2P_DOF 12            /* reference: controller.hpp:13 kDimDOF   */
+#define GO2P_FRAME 49          /* reference: controller.hpp:14 kDimObs   */
+#define GO2P_MAX_HISTORY 8     /* reference uses kHistory = 2 (controller.hpp:15) */
+#define GO2P_MAX_LAYERS 8
+
+typedef struct go2p_handle go2p_handle;
+
+typedef enum go2p_status {
+  GO2P_OK = 0,
+  GO2P_ERR_INVALID = 1,      /* bad argument                                   */
+  GO2P_ERR_IO = 2,           /* model file cannot be read                      */
+  GO2P_ERR_MODEL = 3,        /* .onnx is malformed or uses an unsupported op   */
+  GO2P_ERR_CUDA = 4,         /* a CUDA runtime call failed                     */
+  GO2P_ERR_NO_DEVICE = 5,    /* no sm_100 GPU: there is no CPU fallback        */
+  GO2P_ERR_UNSUPPORTED = 6,  /* valid request the kernels cannot serve         */
+  GO2P_ERR_STATE = 7,        /* call not valid in the current state            */
+  GO2P_ERR_TIMEOUT = 8       /* persistent kernel did not answer               */
+} go2p_status;
+
+/* arithmetic used for the Gemm operands of the batched path (accumulation is always fp32) */
+typedef enum go2p_precision {
+  GO2P_PREC_FP32 = 0,        /* CUDA-core FFMA; agrees with ORT-CPU semantics to 1e-5 */
+  GO2P_PREC_BF16 = 1,        /* tcgen05 kind::f16, bf16 operands                        */
+  GO2P_PREC_FP16 = 2,        /* tcgen05 kind::f16, fp16 operands (saturating convert)   */
+  GO2P_PREC_TF32 = 3         /* tcgen05 kind::tf32                                      */
+} go2p_precision;
+
+/* how the batch-1 control-loop step reaches the GPU */
+typedef enum go2p_b1_mode {
+  GO2P_B1_PERSISTENT = 0,    /* one resident kernel polls a host-mapped mailbox: launch-free */
+  GO2P_B1_GRAPH = 1,         /* one CUDA-graph launch per step, zero-copy mailbox I/O        */
+  GO2P_B1_LAUNCH = 2         /* plain kernel launch per step                                 */
+} go2p_b1_mode;
+
+/* flags of go2p_infer_batch_ex */
+#define GO2P_F_CLAMP_MASK 1u   /* apply A9 (clamp to +-action_limit, multiply by button0==0) */
+#define GO2P_F_QDES 2u         /* also emit A11 q_des = q0 + (double)a * action_scale        */
+
+/* Compile-time constants of the reference exposed as one POD; go2p_config_default()
+ * fills in the reference's values. */
+typedef struct go2p_config {
+  uint32_t struct_size;        /* = sizeof(go2p_config), for ABI evolution                    */
+  int32_t device;              /* CUDA device ordinal (default 0)                             */
+  int32_t b1_mode;             /* go2p_b1_mode (default: env GO2P_B1_MODE or PERSISTENT)      */
+  int32_t history;             /* H; obs width must be 49*H for the fused step (default 2)    */
+  float action_limit;          /* controller.hpp:16  kActionLimit = 1000                      */
+  double action_scale;         /* controller.cpp:244 0.25                                     */
+  double q0[GO2P_DOF];         /* controller.hpp:165                                          */
+  int32_t foot_threshold;      /* controller.hpp:100-103  22                                  */
+  float kp, kd;                /* controller.hpp:119-120  28.0, 0.5                           */
+  float kp_deadman;            /* controller.cpp:246  5                                       */
+  int32_t log_level;           /* OrtLoggingLevel numbering (onnx_actor.hpp:33), 2 = WARNING  */
+  int32_t timeout_ms;          /* persistent-mailbox answer timeout (default 2000)            */
+} go2p_config;
+
+/* Everything publish() reads from the outside world in one control step. */
+typedef struct go2p_raw_state {
+  float quat[4];               /* w,x,y,z  controller.hpp:95-97                               */
+  float gyro[3];               /* controller.hpp:109                                          */
+  float q[GO2P_DOF];           /* (float)robot_interface_->get_q()[i]   controller.cpp:189    */
+  float dq[GO2P_DOF];          /* (float)robot_interface_->get_dq()[i]  controller.cpp:190    */
+  float axes[4];               /* joy axes; 0,1,3 are read  controller.cpp:176-178            */
+  int16_t foot_force[4];       /* unitree order; swapped + thresholded  controller.hpp:100-103*/
+  int32_t joy_valid;           /* joy_ && !joy_->axes.empty()  controller.cpp:173             */
+  int32_t button0;             /* joy_->buttons[0]  controller.cpp:221,246                    */
+} go2p_raw_state;
+
+/* What publish() hands on: the ObservationAction message payload
+ * (onnx_interfaces/msg/ObservationAction.msg:1-2) and the send_command arguments. */
+typedef struct go2p_step_out {
+  float observation[GO2P_FRAME * GO2P_MAX_HISTORY]; /* first 49*H valid                       */
+  float action_raw[GO2P_DOF];  /* policy output before clamp/mask                             */
+  float action[GO2P_DOF];      /* published action (post clamp+mask, pre scaling)             */
+  double q_des[GO2P_DOF];      /* controller.cpp:244                                          */
+  double kp, kd;               /* controller.cpp:246-247 (same value for all 12 joints)       */
+  uint64_t device_ns;          /* in-kernel time from inputs-seen to outputs-written          */
+} go2p_step_out;
+
+typedef struct go2p_model_info_t {
+  int32_t in_dim, out_dim, n_layers;
+  int32_t dims[GO2P_MAX_LAYERS + 1];
+  int32_t has_elu[GO2P_MAX_LAYERS];
+  float elu_alpha[GO2P_MAX_LAYERS];
+  const char* input_name;      /* owned by the handle                                         */
+  const char* output_name;
+  int64_t n_params;
+  int32_t sm_count, cc_major, cc_minor;
+  int32_t tensor_core_path;    /* 1 if the tcgen05 kernels can serve this model               */
+} go2p_model_info_t;
+
+typedef struct go2p_b1_stats {
+  uint64_t steps;
+  uint64_t device_ns_min, device_ns_max, device_ns_sum;
+} go2p_b1_stats;
+
+/* ---- lifecycle -- replaces Ort::Env / Ort::Session construction, onnx_actor.cpp:6-36 ---- */
+void go2p_config_default(go2p_config* cfg);
+int go2p_create(const char* onnx_path, const go2p_config* cfg, go2p_handle** out);
+int go2p_destroy(go2p_handle* h);
+/* replaces session_.GetInputNameAllocated / GetInputTypeInfo ..., onnx_actor.cpp:23-28 */
+int go2p_model_info(const go2p_handle* h, go2p_model_info_t* info);
+const char* go2p_last_error(void);
+int go2p_abi_version(void);
+
+/* ---- batch-1 control loop ---- */
+/* replaces Ort::Value::CreateTensor over the caller's buffers, onnx_actor.cpp:31-35:
+ * the spans are captured; every go2p_act reads obs[0..n_obs) and overwrites act[0..n_act). */
+int go2p_bind(go2p_handle* h, float* obs, size_t n_obs, float* act, size_t n_act);
+/* replaces session_.Run, onnx_actor.cpp:47 (A7 only, synchronous) */
+int go2p_act(go2p_handle* h);
+/* A1-A6 + A7 + A9 + A11 in one device round trip; history lives on the device */
+int go2p_step_fused(go2p_handle* h, const go2p_raw_state* raw, go2p_step_out* out);
+/* controller.hpp:132-162 initial member state: histories 0, action 0, vel_cmd 0 */
+int go2p_reset_history(go2p_handle* h);
+/* ROS params kp/kd, controller.cpp:254-277 */
+int go2p_set_gains(go2p_handle* h, float kp, float kd);
+int go2p_b1_stats_get(go2p_handle* h, go2p_b1_stats* out, int reset);
+/* start/stop the resident kernel explicitly (create starts it lazily on first use) */
+int go2p_persistent_start(go2p_handle* h);
+int go2p_persistent_stop(go2p_handle* h);
+
+/* ---- batched inference: many robots / rollouts through the same policy ---- */
+/* d_obs [B,in_dim] and d_act [B,out_dim] are DEVICE pointers, row-major fp32, the layout of
+ * ObservationAction.msg repeated B times.  Asynchronous on `stream` (a cudaStream_t, may be NULL). */
+int go2p_infer_batch(go2p_handle* h, const float* d_obs, float* d_act, int64_t B,
+                     int precision, void* stream);
+/* + fused A9/A11 epilogue. d_button0 [B] int32 (may be NULL = all 0), d_qdes [B,12] double (may be NULL) */
+int go2p_infer_batch_ex(go2p_handle* h, const float* d_obs, const int32_t* d_button0,
+                        float* d_act, double* d_qdes, int64_t B, int precision,
+                        uint32_t flags, void* stream);
+/* HOST buffers: chunked H2D -> kernel -> D2H pipeline inside the call, synchronous.
+ * h_obs/h_act should be pinned (go2p_host_alloc) for full PCIe rate. */
+int go2p_infer_batch_host(go2p_handle* h, const float* h_obs, float* h_act, int64_t B, int precision);
+/* batched A1-A6 front-end: B robots' raw state -> obs rows, history kept per robot.
+ * d_raw [B] go2p_raw_state, d_prev_action [B,12] (the robots' previous published action),
+ * d_obs [B,49*H] is read (old frames) and rewritten in place. */
+int go2p_assemble_batch(go2p_handle* h, const go2p_raw_state* d_raw, const float* d_prev_action,
+                        float* d_vel_cmd, float* d_obs, int64_t B, void* stream);
+/* number of kernels the previous batched call launched (for bench.py's gpu_launches) */
+int go2p_last_launch_count(const go2p_handle* h);
+
+/* ---- small device / pinned-memory helpers so non-CUDA hosts can drive the batched path ---- */
+int go2p_dev_alloc(go2p_handle* h, size_t bytes, void** dptr);
+int go2p_dev_free(go2p_handle* h, void* dptr);
+int go2p_host_alloc(go2p_handle* h, size_t bytes, void** hptr);   /* pinned */
+int go2p_host_free(go2p_handle* h, void* hptr);
+int go2p_memcpy_h2d(go2p_handle* h, void* dptr, const void* hptr, size_t bytes, void* stream);
+int go2p_memcpy_d2h(go2p_handle* h, void* hptr, const void* dptr, size_t bytes, void* stream);
+int go2p_stream_sync(go2p_handle* h, void* stream);
+/* time `iters` back-to-back go2p_infer_batch_ex launches with CUDA events on `stream` */
+int go2p_time_batch(go2p_handle* h, const float* d_obs, const int32_t* d_button0, float* d_act,
+                    double* d_qdes, int64_t B, int precision, uint32_t flags, void* stream,
+                    int iters, float* total_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GO2POLICY_H */
