@@ -4,7 +4,7 @@ CUDA kernels + C ABI live in csrc/ (built in-tree into lib/); this package is th
 mirror used by the tests and bench.py.  There is no CPU fallback anywhere in this package.
 """
 from .actor import DEFAULT_MODEL, Go2Controller, ONNXActor, PolicyBatch, default_config  # noqa: F401
-from .build import build  # noqa: F401
-from . import capi  # noqa: F401
+from . import build, capi, shard  # noqa: F401
+build_native = build.build
 
-__all__ = ["ONNXActor", "Go2Controller", "PolicyBatch", "default_config", "build", "capi", "DEFAULT_MODEL"]
+__all__ = ["ONNXActor", "Go2Controller", "PolicyBatch", "default_config", "build", "build_native", "capi", "shard", "DEFAULT_MODEL"]

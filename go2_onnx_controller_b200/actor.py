@@ -109,6 +109,18 @@ class Go2Controller:
         capi.check(self._hd.lib.go2p_step_fused(self._hd.h, C.byref(raw), C.byref(out)))
         return out
 
+    def closed_loop(self, raws, steps: int):
+        """`steps` fused steps over the raw states (cycled), timed in native code.
+        Returns (host_ns[steps], device_ns[steps], last StepOut)."""
+        arr = (capi.RawState * len(raws))(*raws)
+        host = np.zeros(steps, np.uint64)
+        dev = np.zeros(steps, np.uint64)
+        last = capi.StepOut()
+        u64 = C.POINTER(C.c_uint64)
+        capi.check(self._hd.lib.go2p_b1_closed_loop(self._hd.h, arr, len(raws), steps, host.ctypes.data_as(u64),
+                                                    dev.ctypes.data_as(u64), C.byref(last)))
+        return host, dev, last
+
     def reset(self) -> None:
         capi.check(self._hd.lib.go2p_reset_history(self._hd.h))
 

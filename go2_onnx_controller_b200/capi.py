@@ -24,7 +24,7 @@ class Config(C.Structure):
         ("struct_size", C.c_uint32), ("device", C.c_int32), ("b1_mode", C.c_int32), ("history", C.c_int32),
         ("action_limit", C.c_float), ("action_scale", C.c_double), ("q0", C.c_double * GO2P_DOF),
         ("foot_threshold", C.c_int32), ("kp", C.c_float), ("kd", C.c_float), ("kp_deadman", C.c_float),
-        ("log_level", C.c_int32), ("timeout_ms", C.c_int32),
+        ("log_level", C.c_int32), ("timeout_ms", C.c_int32), ("idle_exit_ms", C.c_int32),
     ]
 
 
@@ -71,6 +71,8 @@ SIGNATURES = {
     "go2p_bind": (C.c_int, [_H, _fp, C.c_size_t, _fp, C.c_size_t]),
     "go2p_act": (C.c_int, [_H]),
     "go2p_step_fused": (C.c_int, [_H, C.POINTER(RawState), C.POINTER(StepOut)]),
+    "go2p_b1_closed_loop": (C.c_int, [_H, C.POINTER(RawState), C.c_int, C.c_int, C.POINTER(C.c_uint64),
+                                       C.POINTER(C.c_uint64), C.POINTER(StepOut)]),
     "go2p_reset_history": (C.c_int, [_H]),
     "go2p_set_gains": (C.c_int, [_H, C.c_float, C.c_float]),
     "go2p_b1_stats_get": (C.c_int, [_H, C.POINTER(B1Stats), C.c_int]),

@@ -51,7 +51,6 @@ inline void cpu_relax() {
 #endif
 }
 
-constexpr int kOutSlots = 1024;
 constexpr int64_t kFp32ChunkRows = 131072;
 constexpr int64_t kHostChunkRows = 65536;
 constexpr int kPipeDepth = 3;
@@ -83,6 +82,7 @@ struct go2p_handle {
   MailWord* outbox = nullptr;   // host-mapped
   int n_in_slots = 0;
   uint32_t seq = 0;
+  uint32_t epoch = 0;           // launch counter of the resident kernel (farewell word carries it)
   bool resident = false;
   cudaStream_t b1_stream = nullptr;
   cudaGraph_t graph = nullptr;
@@ -242,6 +242,8 @@ B1Args make_b1_args(const go2p_handle* h, bool weights_in_smem) {
   a.outbox = h->outbox;
   a.n_in_slots = h->n_in_slots;
   a.weights_in_smem = weights_in_smem ? 1 : 0;
+  a.idle_ns = (unsigned long long)std::max(0, h->cfg.idle_exit_ms) * 1000000ull;
+  a.epoch = h->epoch;
   return a;
 }
 
@@ -253,6 +255,11 @@ void mail_send(go2p_handle* h, uint32_t type, const uint32_t* words, int n, uint
   *tag_out = tag;
 }
 
+bool resident_said_goodbye(const go2p_handle* h) {
+  const volatile uint64_t* slots = reinterpret_cast<const volatile uint64_t*>(h->outbox);
+  return slots[kByeSlot] == (((uint64_t)kByeTag << 32) | (uint64_t)h->epoch);
+}
+
 int mail_wait(go2p_handle* h, uint32_t tag, int n_words) {
   const volatile uint64_t* slots = reinterpret_cast<const volatile uint64_t*>(h->outbox);
   const auto t0 = std::chrono::steady_clock::now();
@@ -260,7 +267,13 @@ int mail_wait(go2p_handle* h, uint32_t tag, int n_words) {
   for (int i = n_words - 1; i >= 0; --i) {
     while ((uint32_t)(slots[i] >> 32) != tag) {
       cpu_relax();
-      if ((++spins & 0xFFFF) == 0) {
+      if ((++spins & 0xFF) == 0 && h->resident && resident_said_goodbye(h)) {
+        // the kernel timed out idle while this request was in flight: relaunch, it will pick the request up
+        h->resident = false;
+        int rc = go2p_persistent_start(h);
+        if (rc) return rc;
+      }
+      if ((spins & 0xFFFF) == 0) {
         const auto dt = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
         if (dt > h->cfg.timeout_ms) {
           cudaError_t e = cudaPeekAtLastError();
@@ -277,6 +290,7 @@ int mail_wait(go2p_handle* h, uint32_t tag, int n_words) {
 int b1_dispatch(go2p_handle* h) {
   // called after mail_send: make sure some kernel will consume the message
   if (h->cfg.b1_mode == GO2P_B1_PERSISTENT) {
+    if (h->resident && resident_said_goodbye(h)) h->resident = false;
     if (!h->resident) return go2p_persistent_start(h);
     return GO2P_OK;
   }
@@ -442,6 +456,8 @@ void go2p_config_default(go2p_config* c) {
   c->kp_deadman = 5.0f;                             // controller.cpp:246
   c->log_level = 2;
   c->timeout_ms = 2000;
+  c->idle_exit_ms = 30000;
+  if (const char* e = std::getenv("GO2P_IDLE_EXIT_MS")) c->idle_exit_ms = std::atoi(e);
 }
 
 int go2p_create(const char* onnx_path, const go2p_config* cfg_in, go2p_handle** out) {
@@ -568,6 +584,7 @@ int go2p_persistent_start(go2p_handle* h) {
   bool fit = false;
   const size_t smem = b1_smem_bytes(h, true, &fit);
   CU_TRY(cudaFuncSetAttribute(b1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ++h->epoch;
   B1Args a = make_b1_args(h, fit);
   b1_kernel<true><<<1, kB1Threads, smem, h->b1_stream>>>(a);
   CU_TRY(cudaGetLastError());
@@ -581,6 +598,11 @@ int go2p_persistent_stop(go2p_handle* h) {
   if (!h) return fail(GO2P_ERR_INVALID, "null handle");
   if (!h->resident) return GO2P_OK;
   DeviceGuard g(h->device);
+  if (resident_said_goodbye(h)) {
+    h->resident = false;
+    CU_TRY(cudaStreamSynchronize(h->b1_stream));
+    return GO2P_OK;
+  }
   uint32_t tag;
   mail_send(h, MSG_EXIT, nullptr, 0, &tag);
   int rc = mail_wait(h, tag, 1);
@@ -652,6 +674,22 @@ int go2p_step_fused(go2p_handle* h, const go2p_raw_state* raw, go2p_step_out* ou
   out->kd = f64(n_obs + 50);
   out->device_ns = (uint64_t)ob[n_obs + 52].bits | ((uint64_t)ob[n_obs + 53].bits << 32);
   stats_add(h, out->device_ns);
+  return GO2P_OK;
+}
+
+int go2p_b1_closed_loop(go2p_handle* h, const go2p_raw_state* raws, int n_raws, int steps, uint64_t* host_ns,
+                        uint64_t* device_ns, go2p_step_out* last) {
+  if (!h || !raws || n_raws < 1 || steps < 0) return fail(GO2P_ERR_INVALID, "go2p_b1_closed_loop: bad argument");
+  go2p_step_out out;
+  for (int i = 0; i < steps; ++i) {
+    const auto t0 = std::chrono::steady_clock::now();
+    const int rc = go2p_step_fused(h, &raws[i % n_raws], &out);
+    const auto t1 = std::chrono::steady_clock::now();
+    if (rc) return rc;
+    if (host_ns) host_ns[i] = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
+    if (device_ns) device_ns[i] = out.device_ns;
+  }
+  if (last && steps > 0) *last = out;
   return GO2P_OK;
 }
 

@@ -43,7 +43,15 @@ struct B1Args {
   int n_in_slots;           // slots the host fills for every message (multiple of 32)
   int weights_in_smem;      // resident kernel only
   int smem_weight_floats;
+  // resident kernel only: leave the SM after this long without a message (0 = never).  The host sees
+  // the farewell word {epoch, kByeTag} in outbox[kByeSlot] and relaunches on the next request, so an
+  // abandoned handle can never pin an SM (or hang a GPU box) for longer than this.
+  unsigned long long idle_ns;
+  uint32_t epoch;
 };
+constexpr int kOutSlots = 1024;
+constexpr int kByeSlot = kOutSlots - 1;
+constexpr uint32_t kByeTag = 0xB1E0B1E0u;
 
 __device__ __forceinline__ uint2 ld_mail(const MailWord* p) {
   uint2 v;
@@ -208,12 +216,16 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_kernel(const B1Args a) {
   uint32_t* rw = reinterpret_cast<uint32_t*>(part + kB1Threads);
   B1State* st = a.gstate;
   const float* wsm = nullptr;
+  __shared__ uint32_t s_type;
+  __shared__ uint64_t s_t0;
+  __shared__ volatile int s_quit;
 
   if (kResident) {
     B1State* sst = reinterpret_cast<B1State*>(rw + 64);
     for (int i = tid; i < (int)(sizeof(B1State) / 4); i += kB1Threads)
       reinterpret_cast<uint32_t*>(sst)[i] = reinterpret_cast<const uint32_t*>(a.gstate)[i];
     st = sst;
+    if (tid == 0) s_quit = 0;
     if (a.weights_in_smem) {
       // weights (in the layout each layer reads) and biases become shared-memory resident for the
       // life of the kernel: a control step touches no global/HBM weight byte.
@@ -244,16 +256,38 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_kernel(const B1Args a) {
     uint32_t type = 0;
     if (tid < a.n_in_slots) {
       uint2 mw;
-      do { mw = ld_mail(a.inbox + tid); } while ((mw.y >> 3) != (want & 0x1FFFFFFFu));
+      if (kResident && a.idle_ns != 0ull) {
+        uint32_t polls = 0;
+        uint64_t idle0 = 0;
+        for (;;) {
+          mw = ld_mail(a.inbox + tid);
+          if ((mw.y >> 3) == (want & 0x1FFFFFFFu) || s_quit) break;
+          if (tid == 0 && (++polls & 0xFFu) == 0u) {
+            const uint64_t now = globaltimer_ns();
+            if (idle0 == 0) idle0 = now;
+            else if (now - idle0 > a.idle_ns) { s_quit = 1; break; }
+          }
+        }
+      } else {
+        do { mw = ld_mail(a.inbox + tid); } while ((mw.y >> 3) != (want & 0x1FFFFFFFu));
+      }
       type = mw.y & 7u;
       if (tid < 64) rw[tid] = mw.x;
       xa[tid] = __uint_as_float(mw.x);   // ACT payload == observation (overwritten for STEP); n_in_slots <= XW
     }
     // message type is uniform across slots; broadcast from thread 0 through shared memory
-    __shared__ uint32_t s_type;
-    __shared__ uint64_t s_t0;
     if (tid == 0) { s_type = type; s_t0 = globaltimer_ns(); }
     __syncthreads();
+    if (kResident && s_quit) {
+      // idle farewell: state goes back to device memory, sequence number untouched -> a message that
+      // raced with the timeout is served by the relaunched kernel
+      for (int i = tid; i < (int)(sizeof(B1State) / 4); i += kB1Threads)
+        reinterpret_cast<uint32_t*>(a.gstate)[i] = reinterpret_cast<const uint32_t*>(st)[i];
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) st_mail(a.outbox + kByeSlot, a.epoch, kByeTag);
+      return;
+    }
     type = s_type;
     const uint32_t tag = make_tag(want, type);
 

@@ -82,6 +82,8 @@ typedef struct go2p_config {
   float kp_deadman;            /* controller.cpp:246  5                                       */
   int32_t log_level;           /* OrtLoggingLevel numbering (onnx_actor.hpp:33), 2 = WARNING  */
   int32_t timeout_ms;          /* persistent-mailbox answer timeout (default 2000)            */
+  int32_t idle_exit_ms;        /* resident kernel leaves its SM after this long without a     *
+                                * request and is relaunched on demand (default 30000, 0=never)*/
 } go2p_config;
 
 /* Everything publish() reads from the outside world in one control step. */
@@ -141,6 +143,12 @@ int go2p_bind(go2p_handle* h, float* obs, size_t n_obs, float* act, size_t n_act
 int go2p_act(go2p_handle* h);
 /* A1-A6 + A7 + A9 + A11 in one device round trip; history lives on the device */
 int go2p_step_fused(go2p_handle* h, const go2p_raw_state* raw, go2p_step_out* out);
+/* `steps` consecutive go2p_step_fused calls over raws[i % n_raws] (closed loop: the device feeds its own
+ * previous action back), each timed on the host with a monotonic clock from request-written to
+ * answer-read.  host_ns / device_ns (may be NULL) receive one entry per step; last (may be NULL) the
+ * final step's output.  Measurement helper for BASELINE.json configs[1]. */
+int go2p_b1_closed_loop(go2p_handle* h, const go2p_raw_state* raws, int n_raws, int steps,
+                        uint64_t* host_ns, uint64_t* device_ns, go2p_step_out* last);
 /* controller.hpp:132-162 initial member state: histories 0, action 0, vel_cmd 0 */
 int go2p_reset_history(go2p_handle* h);
 /* ROS params kp/kd, controller.cpp:254-277 */

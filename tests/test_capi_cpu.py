@@ -1,0 +1,128 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/go2policy.h
+declares, parses models on the host, and refuses to compute without an sm_100 device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from go2_onnx_controller_b200 import actor, build, capi
+from oracle import onnx_mini
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _no_gpu():
+    import torch
+    return not torch.cuda.is_available()
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return capi.load()
+
+
+def test_header_symbols_all_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "go2policy.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(go2p_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    assert declared == set(capi.SIGNATURES), declared ^ set(capi.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    nm = subprocess.run(["nm", "-D", "--defined-only", build.LIB], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (go2p_[a-z0-9_]+)", nm))
+    assert declared <= exported
+
+
+def test_abi_version_and_config_defaults(lib):
+    assert lib.go2p_abi_version() == 1
+    cfg = actor.default_config()
+    # reference constants: controller.hpp:13-16,100-103,119-120,165; controller.cpp:244,246
+    assert cfg.struct_size == C.sizeof(capi.Config)
+    assert cfg.history == 2 and cfg.action_limit == 1000.0 and cfg.action_scale == 0.25
+    assert list(cfg.q0) == [0.1, -0.1, 0.1, -0.1, 0.8, 0.8, 1.0, 1.0, -1.5, -1.5, -1.5, -1.5]
+    assert cfg.foot_threshold == 22 and cfg.kp == 28.0 and cfg.kd == 0.5 and cfg.kp_deadman == 5.0
+    assert cfg.log_level == 2     # ORT_LOGGING_LEVEL_WARNING, onnx_actor.hpp:33
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(capi.RawState) == 4 * 35 + 8 + 8
+    assert C.sizeof(capi.StepOut) == 4 * (49 * 8) + 48 + 48 + 96 + 16 + 8
+
+
+def _create(lib, path, cfg=None):
+    h = C.c_void_p()
+    cfg = cfg or actor.default_config()
+    rc = lib.go2p_create(os.fspath(path).encode(), C.byref(cfg), C.byref(h))
+    return rc, h, lib.go2p_last_error().decode()
+
+
+def test_missing_model_is_io_error(lib, tmp_path):
+    rc, h, msg = _create(lib, tmp_path / "nope.onnx")
+    assert rc == capi.ERR_IO and not h and "nope.onnx" in msg
+
+
+def test_garbage_model_is_model_error(lib, tmp_path):
+    p = tmp_path / "bad.onnx"
+    p.write_bytes(b"\x00\x01garbage that is not a protobuf" * 10)
+    rc, h, msg = _create(lib, p)
+    assert rc == capi.ERR_MODEL and not h and msg
+
+
+def test_unsupported_op_is_rejected(lib, tmp_path):
+    ws = [np.ones((4, 3), np.float32), np.ones((2, 4), np.float32)]
+    bs = [np.zeros(4, np.float32), np.zeros(2, np.float32)]
+    blob = onnx_mini.write_mlp_onnx(ws, bs, 1.0).replace(b"Elu", b"Erf")
+    p = tmp_path / "erf.onnx"
+    p.write_bytes(blob)
+    rc, h, msg = _create(lib, p)
+    assert rc == capi.ERR_MODEL and "Erf" in msg
+
+
+def test_struct_size_mismatch_is_invalid(lib, model_path):
+    cfg = actor.default_config()
+    cfg.struct_size = 8
+    rc, h, msg = _create(lib, model_path, cfg)
+    assert rc == capi.ERR_INVALID and "struct_size" in msg
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="checks the no-device behaviour")
+def test_no_device_means_no_compute(lib, model_path):
+    """The product has no CPU fallback: a valid model without an sm_100 device fails loudly."""
+    rc, h, msg = _create(lib, model_path)
+    assert rc == capi.ERR_NO_DEVICE and not h
+    assert "no CPU fallback" in msg or "sm_100a" in msg
+    obs, act = np.zeros(98, np.float32), np.zeros(12, np.float32)
+    with pytest.raises(capi.Go2PolicyError) as e:
+        actor.ONNXActor(model_path, obs, act)
+    assert e.value.code == capi.ERR_NO_DEVICE
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="checks the no-device behaviour")
+def test_cpp_class_throws_without_device(model_path):
+    """The reference-compatible C++ class (include/onnx_actor.hpp) surfaces the failure as std::exception,
+    like the reference's Ort::Exception out of the constructor (onnx_actor.cpp:16)."""
+    r = subprocess.run([build.SMOKE, model_path], capture_output=True, text=True)
+    assert r.returncode == 1 and "ONNXActor" in r.stderr
+
+
+def test_null_arguments_are_errors(lib):
+    assert lib.go2p_act(None) == capi.ERR_INVALID
+    assert lib.go2p_destroy(None) == capi.OK
+    assert lib.go2p_infer_batch(None, None, None, 1, 0, None) == capi.ERR_INVALID
+    assert lib.go2p_last_launch_count(None) == 0
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under the package may import, link or open it."""
+    pkg = os.path.join(ROOT, "go2_onnx_controller_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "liboracle" not in src and "oracle/" not in src, f
