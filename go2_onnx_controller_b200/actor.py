@@ -121,6 +121,16 @@ class Go2Controller:
                                                     dev.ctypes.data_as(u64), C.byref(last)))
         return host, dev, last
 
+    def selfdriven(self, raws, steps: int):
+        """Profiling twin of the resident kernel: one bounded launch of `steps` closed-loop steps.
+        Returns (last published action[12], elapsed ms)."""
+        arr = (capi.RawState * len(raws))(*raws)
+        act = np.zeros(12, np.float32)
+        ms = C.c_float()
+        capi.check(self._hd.lib.go2p_b1_selfdriven(self._hd.h, arr, len(raws), steps,
+                                                   act.ctypes.data_as(C.POINTER(C.c_float)), C.byref(ms)))
+        return act, float(ms.value)
+
     def reset(self) -> None:
         capi.check(self._hd.lib.go2p_reset_history(self._hd.h))
 

@@ -17,7 +17,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
-LIB = os.path.join(LIBDIR, "libgo2policy.so")
+LIB = os.environ.get("GO2P_LIB") or os.path.join(LIBDIR, "libgo2policy.so")
 ACTOR_LIB = os.path.join(LIBDIR, "libonnx_actor.so")
 SMOKE = os.path.join(LIBDIR, "go2_smoke")
 

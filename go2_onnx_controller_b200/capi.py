@@ -73,6 +73,7 @@ SIGNATURES = {
     "go2p_step_fused": (C.c_int, [_H, C.POINTER(RawState), C.POINTER(StepOut)]),
     "go2p_b1_closed_loop": (C.c_int, [_H, C.POINTER(RawState), C.c_int, C.c_int, C.POINTER(C.c_uint64),
                                        C.POINTER(C.c_uint64), C.POINTER(StepOut)]),
+    "go2p_b1_selfdriven": (C.c_int, [_H, C.POINTER(RawState), C.c_int, C.c_int, _fp, _fp]),
     "go2p_reset_history": (C.c_int, [_H]),
     "go2p_set_gains": (C.c_int, [_H, C.c_float, C.c_float]),
     "go2p_b1_stats_get": (C.c_int, [_H, C.POINTER(B1Stats), C.c_int]),

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -73,9 +74,11 @@ struct go2p_handle {
   WideModel wide{};
   uint32_t tc_debug = 0;
   int tc_epw = 4;
-  // fp32 path scratch
-  float* scratch[2] = {nullptr, nullptr};
-  int64_t scratch_rows = 0;
+  // fp32 path scratch (activations between the per-layer launches): set 0 serves the device-pointer API,
+  // sets 1..kPipeDepth the streams of the host-buffer pipeline (which run concurrently)
+  struct Scratch { float* buf[2] = {nullptr, nullptr}; int64_t rows = 0; };
+  Scratch scratch_sets[1 + kPipeDepth];
+  int scratch_sel = 0;
   // batch-1
   B1State* d_state = nullptr;
   MailWord* inbox = nullptr;    // host-mapped
@@ -284,6 +287,7 @@ int mail_wait(go2p_handle* h, uint32_t tag, int n_words) {
       }
     }
   }
+  std::atomic_thread_fence(std::memory_order_acquire);   // payload reads below stay after the tag polls
   return GO2P_OK;
 }
 
@@ -338,15 +342,17 @@ int simple_message(go2p_handle* h, uint32_t type, const uint32_t* words, int n) 
 }
 
 int ensure_scratch(go2p_handle* h, int64_t rows) {
-  if (h->scratch_rows >= rows) return GO2P_OK;
+  go2p_handle::Scratch& sc = h->scratch_sets[h->scratch_sel];
+  if (sc.rows >= rows) return GO2P_OK;
   for (int i = 0; i < 2; ++i) {
-    if (h->scratch[i]) cudaFree(h->scratch[i]);
-    h->scratch[i] = nullptr;
+    if (sc.buf[i]) cudaFree(sc.buf[i]);
+    sc.buf[i] = nullptr;
   }
+  sc.rows = 0;
   const size_t bytes = (size_t)rows * h->dm.max_width * sizeof(float);
-  CU_TRY(cudaMalloc((void**)&h->scratch[0], bytes));
-  CU_TRY(cudaMalloc((void**)&h->scratch[1], bytes));
-  h->scratch_rows = rows;
+  CU_TRY(cudaMalloc((void**)&sc.buf[0], bytes));
+  CU_TRY(cudaMalloc((void**)&sc.buf[1], bytes));
+  sc.rows = rows;
   return GO2P_OK;
 }
 
@@ -363,7 +369,7 @@ int launch_fp32(go2p_handle* h, const float* d_obs, const int32_t* d_button0, fl
     for (int l = 0; l < dm.n_layers; ++l) {
       const DevLayer& L = dm.L[l];
       const bool last = l == dm.n_layers - 1;
-      float* out = last ? d_act + r0 * dm.out_dim : h->scratch[l & 1];
+      float* out = last ? d_act + r0 * dm.out_dim : h->scratch_sets[h->scratch_sel].buf[l & 1];
       const int ldc = L.N;
       if (last && L.N <= 32) {
         const size_t smem = ((size_t)kSoRows * (L.K | 1) + (size_t)L.N * L.Kp) * sizeof(float);
@@ -546,7 +552,8 @@ int go2p_destroy(go2p_handle* h) {
   }
   if (h->b1_stream) cudaStreamDestroy(h->b1_stream);
   for (void* p : h->dev_owned) cudaFree(p);
-  for (int i = 0; i < 2; ++i) if (h->scratch[i]) cudaFree(h->scratch[i]);
+  for (auto& sc : h->scratch_sets)
+    for (int i = 0; i < 2; ++i) if (sc.buf[i]) cudaFree(sc.buf[i]);
   if (h->d_state) cudaFree(h->d_state);
   if (h->inbox) cudaFreeHost(h->inbox);
   if (h->outbox) cudaFreeHost(h->outbox);
@@ -693,6 +700,56 @@ int go2p_b1_closed_loop(go2p_handle* h, const go2p_raw_state* raws, int n_raws, 
   return GO2P_OK;
 }
 
+int go2p_b1_selfdriven(go2p_handle* h, const go2p_raw_state* raws, int n_raws, int steps, float* last_action,
+                       float* elapsed_ms) {
+  if (!h || !raws || n_raws < 1 || steps < 1) return fail(GO2P_ERR_INVALID, "go2p_b1_selfdriven: bad argument");
+  if (h->dm.in_dim != GO2P_FRAME * h->cfg.history || h->dm.out_dim != GO2P_DOF)
+    return fail(GO2P_ERR_UNSUPPORTED, "fused step needs a policy with 49*history inputs and 12 outputs");
+  DeviceGuard g(h->device);
+  bool fit = false;
+  const size_t smem = b1_smem_bytes(h, true, &fit);
+  if (!fit) return fail(GO2P_ERR_UNSUPPORTED, "weights do not fit shared memory");
+  std::vector<uint32_t> words((size_t)n_raws * kRawWords);
+  for (int r = 0; r < n_raws; ++r) {
+    uint32_t* w = &words[(size_t)r * kRawWords];
+    std::memcpy(&w[0], raws[r].quat, 16); std::memcpy(&w[4], raws[r].gyro, 12);
+    std::memcpy(&w[7], raws[r].q, 48); std::memcpy(&w[19], raws[r].dq, 48); std::memcpy(&w[31], raws[r].axes, 16);
+    for (int i = 0; i < 4; ++i) w[35 + i] = (uint32_t)(int32_t)raws[r].foot_force[i];
+    w[39] = (uint32_t)(raws[r].joy_valid != 0);
+    w[40] = (uint32_t)raws[r].button0;
+  }
+  uint32_t* d_raws = nullptr;
+  float* d_out = nullptr;
+  B1State* d_st = nullptr;
+  CU_TRY(cudaMalloc((void**)&d_raws, words.size() * 4));
+  CU_TRY(cudaMalloc((void**)&d_out, 64));
+  CU_TRY(cudaMalloc((void**)&d_st, sizeof(B1State)));
+  B1State init{};
+  init.kp = h->cfg.kp; init.kd = h->cfg.kd;
+  CU_TRY(cudaMemcpy(d_st, &init, sizeof(init), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(d_raws, words.data(), words.size() * 4, cudaMemcpyHostToDevice));
+  CU_TRY(cudaFuncSetAttribute(b1_selfdriven_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B1Args a = make_b1_args(h, true);
+  a.gstate = d_st;
+  cudaEvent_t e0, e1;
+  CU_TRY(cudaEventCreate(&e0));
+  CU_TRY(cudaEventCreate(&e1));
+  CU_TRY(cudaEventRecord(e0, h->pipe_stream[0]));
+  b1_selfdriven_kernel<<<1, kB1Threads, smem, h->pipe_stream[0]>>>(a, d_raws, n_raws, steps, d_out);
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaEventRecord(e1, h->pipe_stream[0]));
+  CU_TRY(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  if (elapsed_ms) *elapsed_ms = ms;
+  if (last_action) CU_TRY(cudaMemcpyAsync(last_action, d_out, 48, cudaMemcpyDeviceToHost, h->pipe_stream[0]));
+  CU_TRY(cudaStreamSynchronize(h->pipe_stream[0]));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (!h->resident) { cudaFree(d_raws); cudaFree(d_out); cudaFree(d_st); }   // cudaFree would block on a resident kernel
+  h->last_launches = 1;
+  return GO2P_OK;
+}
+
 int go2p_reset_history(go2p_handle* h) {
   if (!h) return fail(GO2P_ERR_INVALID, "null handle");
   return simple_message(h, MSG_RESET, nullptr, 0);
@@ -717,8 +774,10 @@ int go2p_b1_stats_get(go2p_handle* h, go2p_b1_stats* out, int reset) {
 // ------------------------------------------------------------------------------------- batched
 int go2p_infer_batch_ex(go2p_handle* h, const float* d_obs, const int32_t* d_button0, float* d_act, double* d_qdes,
                         int64_t B, int precision, uint32_t flags, void* stream) {
-  if (!h || !d_obs || !d_act) return fail(GO2P_ERR_INVALID, "go2p_infer_batch: null argument");
+  if (!h) return fail(GO2P_ERR_INVALID, "go2p_infer_batch: null handle");
   if (B < 0) return fail(GO2P_ERR_INVALID, "negative batch");
+  if (B == 0) { h->last_launches = 0; return GO2P_OK; }   // empty batch: nothing is read, nothing is launched
+  if (!d_obs || !d_act) return fail(GO2P_ERR_INVALID, "go2p_infer_batch: null argument");
   if ((flags & GO2P_F_QDES) && (!d_qdes || h->dm.out_dim != GO2P_DOF))
     return fail(GO2P_ERR_INVALID, "GO2P_F_QDES needs d_qdes and a 12-output policy");
   h->last_launches = 0;
@@ -770,7 +829,9 @@ int go2p_infer_batch_host(go2p_handle* h, const float* h_obs, float* h_act, int6
     const int64_t rows = std::min(chunk, B - r0);
     cudaStream_t st = h->pipe_stream[slot];
     CU_TRY(cudaMemcpyAsync(h->pipe_in[slot], h_obs + r0 * in, (size_t)rows * in * sizeof(float), cudaMemcpyHostToDevice, st));
+    h->scratch_sel = 1 + slot;
     int rc = go2p_infer_batch_ex(h, h->pipe_in[slot], nullptr, h->pipe_out[slot], nullptr, rows, precision, 0u, st);
+    h->scratch_sel = 0;
     if (rc) return rc;
     launches += h->last_launches;
     CU_TRY(cudaMemcpyAsync(h_act + r0 * out, h->pipe_out[slot], (size_t)rows * out * sizeof(float), cudaMemcpyDeviceToHost, st));

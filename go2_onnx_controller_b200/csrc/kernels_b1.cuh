@@ -152,7 +152,7 @@ __device__ __forceinline__ void b1_layer(const DevLayer& L, const float* __restr
         acc = (a0 + a1) + (a2 + a3);
       }
       if (g < G) part[g * Npad + o] = acc;
-      __syncthreads();
+      block_sync();
       if (tid < Nq) {
         float s = 0.f;
         if (tid < L.N) {
@@ -199,7 +199,7 @@ __device__ __forceinline__ void b1_layer(const DevLayer& L, const float* __restr
       if (lane == 0) y[o] = s;
     }
   }
-  __syncthreads();
+  block_sync();
 }
 
 // Dynamic shared memory layout (floats): xa[XW] xb[XW] part[kB1Threads] raw[64] state weights...
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_kernel(const B1Args a) {
       }
       wsm = w;
     }
-    __syncthreads();
+    block_sync();
   }
 
   const int H = a.cc.H;
@@ -277,14 +277,14 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_kernel(const B1Args a) {
     }
     // message type is uniform across slots; broadcast from thread 0 through shared memory
     if (tid == 0) { s_type = type; s_t0 = globaltimer_ns(); }
-    __syncthreads();
+    block_sync();
     if (kResident && s_quit) {
       // idle farewell: state goes back to device memory, sequence number untouched -> a message that
       // raced with the timeout is served by the relaunched kernel
       for (int i = tid; i < (int)(sizeof(B1State) / 4); i += kB1Threads)
         reinterpret_cast<uint32_t*>(a.gstate)[i] = reinterpret_cast<const uint32_t*>(st)[i];
       __threadfence();
-      __syncthreads();
+      block_sync();
       if (tid == 0) st_mail(a.outbox + kByeSlot, a.epoch, kByeTag);
       return;
     }
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_kernel(const B1Args a) {
 
     if (type == MSG_EXIT) {
       if (tid == 0) st->seq = want;
-      __syncthreads();
+      block_sync();
       if (kResident)
         for (int i = tid; i < (int)(sizeof(B1State) / 4); i += kB1Threads)
           reinterpret_cast<uint32_t*>(a.gstate)[i] = reinterpret_cast<const uint32_t*>(st)[i];
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_kernel(const B1Args a) {
         st->kd = __uint_as_float(rw[1]);
       }
       if (tid == 0) { st->seq = want; st_mail(a.outbox, 0u, tag); }
-      __syncthreads();
+      block_sync();
       if (!kResident) return;
       continue;
     }
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_kernel(const B1Args a) {
         newest = (f == H - 1);
         v = newest ? current_term_value(t, c, rw, st, a.cc) : st->obs[tid + wdt];
       }
-      __syncthreads();
+      block_sync();
       if (tid < n_obs) {
         st->obs[tid] = v;
         xa[tid] = v;
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_kernel(const B1Args a) {
     }
     // zero the K padding of the first layer input
     if (tid >= a.model.in_dim && tid < a.model.L[0].Kp) xa[tid] = 0.f;
-    __syncthreads();
+    block_sync();
 
     // ---- A7: Gemm/Elu chain
     float* x = xa;
@@ -393,14 +393,14 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_kernel(const B1Args a) {
         st_mail(ob + n_obs + 52, (uint32_t)dns, tag); st_mail(ob + n_obs + 53, (uint32_t)(dns >> 32), tag);
       }
     }
-    __syncthreads();
+    block_sync();
     if (type == MSG_STEP && tid < kDof) {
       // the published action feeds action_hist_ on the next step (controller.cpp:206)
       const float araw = x[tid];
       st->action[tid] = clamp_mask(araw, a.cc.action_limit, (int)rw[40]);
     }
     if (tid == 0) st->seq = want;
-    __syncthreads();
+    block_sync();
     if (!kResident) return;
   }
 }
@@ -433,11 +433,11 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_selfdriven_kernel(const B1Ar
       off += nb;
     }
   }
-  __syncthreads();
+  block_sync();
   const int H = a.cc.H, n_obs = kFrame * H;
   for (int s = 0; s < steps; ++s) {
     if (tid < kRawWords) rw[tid] = raws[(size_t)(s % n_raws) * kRawWords + tid];
-    __syncthreads();
+    block_sync();
     float v = 0.f; int t = 0, c = 0; bool newest = false;
     if (tid < n_obs) {
       int off, wdt;
@@ -448,10 +448,10 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_selfdriven_kernel(const B1Ar
       newest = (f == H - 1);
       v = newest ? current_term_value(t, c, rw, st, a.cc) : st->obs[tid + wdt];
     }
-    __syncthreads();
+    block_sync();
     if (tid < n_obs) { st->obs[tid] = v; xa[tid] = v; if (newest && t == 2) st->vel_cmd[c] = v; }
     if (tid >= a.model.in_dim && tid < a.model.L[0].Kp) xa[tid] = 0.f;
-    __syncthreads();
+    block_sync();
     float* x = xa; float* y = xb; int woff = 0;
     for (int l = 0; l < a.model.n_layers; ++l) {
       const DevLayer& L = a.model.L[l];
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_selfdriven_kernel(const B1Ar
       st->action[tid] = act;
       if (s == steps - 1) out_actions[tid] = act;
     }
-    __syncthreads();
+    block_sync();
   }
 }
 

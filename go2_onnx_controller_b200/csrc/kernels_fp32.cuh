@@ -56,7 +56,7 @@ sgemm_bias_act_kernel(const float* __restrict__ A, int lda, const float* __restr
 
   gload(0);
   sstore(0);
-  __syncthreads();
+  block_sync();
   for (int kt = 0; kt < Kt; ++kt) {
     const int buf = kt & 1;
     if (kt + 1 < Kt) gload(kt + 1);
@@ -75,7 +75,7 @@ sgemm_bias_act_kernel(const float* __restrict__ A, int lda, const float* __restr
     }
     if (kt + 1 < Kt) {
       sstore(buf ^ 1);
-      __syncthreads();
+      block_sync();
     }
   }
   // epilogue: rows {ty*4..+3, 64+ty*4..+3}, cols {tx*4..+3, 64+tx*4..+3}
@@ -124,7 +124,7 @@ small_out_kernel(const float* __restrict__ A, int lda, const float* __restrict__
     As[r * pitch + k] = A[(size_t)(row0 + r) * lda + k];
   }
   for (int i = tid; i < N * Kp; i += kSoRows) Ws[i] = Wrm[i];
-  __syncthreads();
+  block_sync();
   if (tid >= rows) return;
   const float* x = As + tid * pitch;
   float acc[32];
@@ -198,12 +198,12 @@ __global__ void assemble_batch_kernel(const RawStateDev* __restrict__ raw, const
         }
       }
     }
-    __syncthreads();
+    block_sync();
     if (tid < n_obs) {
       o[tid] = v;
       if (newest && t == 2) vel_cmd[row * 3 + c] = v;
     }
-    __syncthreads();
+    block_sync();
   }
 }
 

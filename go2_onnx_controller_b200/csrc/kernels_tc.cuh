@@ -127,7 +127,7 @@ __global__ void __launch_bounds__((kTcCtrlWarps + 2 * kEpw) * 32, 1) tc_mlp_kern
   }
   ptx::fence_proxy_async_smem();   // weights were written through the generic proxy; UMMA reads via the async proxy
   ptx::tc_fence_before();
-  __syncthreads();
+  block_sync();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__((kTcCtrlWarps + 2 * kEpw) * 32, 1) tc_mlp_kern
 
   // ---- teardown
   ptx::tc_fence_before();
-  __syncthreads();
+  block_sync();
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<512>(tmem_base);

@@ -35,6 +35,16 @@ struct CtrlConst {
   int H;
 };
 
+// CTA barrier that is safe after thread-divergent code.  Measured on B200 (driver 580, CUDA 12.9): when nvcc
+// emits no reconvergence point between an `if (tid < n) {...}` and the following BAR.SYNC, a warp reaches the
+// barrier in two pieces and each piece is counted as an arrival of the whole warp, which skews every later
+// barrier of that warp by one phase (seen as stale shared-memory reads in the one-shot batch-1 kernel).
+// Re-converging the warp first makes the arrival count exact.
+__device__ __forceinline__ void block_sync() {
+  __syncwarp();
+  __syncthreads();
+}
+
 // std::clamp(a,-lim,lim) then a *= (button0==0)   (controller.cpp:218-223)
 // NaN passes through the clamp (no fminf/fmaxf!), the multiply keeps the sign of zero.
 __device__ __forceinline__ float clamp_mask(float a, float lim, int button0) {

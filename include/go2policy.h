@@ -149,6 +149,12 @@ int go2p_step_fused(go2p_handle* h, const go2p_raw_state* raw, go2p_step_out* ou
  * final step's output.  Measurement helper for BASELINE.json configs[1]. */
 int go2p_b1_closed_loop(go2p_handle* h, const go2p_raw_state* raws, int n_raws, int steps,
                         uint64_t* host_ns, uint64_t* device_ns, go2p_step_out* last);
+/* Profiling twin of the resident kernel: ONE bounded launch that runs `steps` closed-loop control steps with
+ * the raw states read from device memory (cycled) and weights/history in shared memory -- what a profiler
+ * can measure of the resident design (a kernel that never exits cannot be profiled): per-step device time =
+ * elapsed_ms/steps, DRAM bytes per step from ncu.  last_action: host float[12] (may be NULL). */
+int go2p_b1_selfdriven(go2p_handle* h, const go2p_raw_state* raws, int n_raws, int steps,
+                       float* last_action, float* elapsed_ms);
 /* controller.hpp:132-162 initial member state: histories 0, action 0, vel_cmd 0 */
 int go2p_reset_history(go2p_handle* h);
 /* ROS params kp/kd, controller.cpp:254-277 */
