@@ -69,11 +69,8 @@ struct go2p_handle {
   bool tc_ok = false;
   bool wide_ok = false;
   uint16_t* d_wpack[2] = {nullptr, nullptr};   // [0] bf16, [1] fp16
-  float* d_bias_tc = nullptr;
   int k0p = 0;
   WideModel wide{};
-  uint32_t tc_debug = 0;
-  int tc_epw = 4;
   // fp32 path scratch (activations between the per-layer launches): set 0 serves the device-pointer API,
   // sets 1..kPipeDepth the streams of the host-buffer pipeline (which run concurrently)
   struct Scratch { float* buf[2] = {nullptr, nullptr}; int64_t rows = 0; };
@@ -136,16 +133,31 @@ uint16_t to_f16(float f) {
   return __half_as_ushort(__float2half_rn(f));
 }
 
+float from_bf16(uint16_t b) { return __bfloat162float(__ushort_as_bfloat16(b)); }
+float from_f16(uint16_t b) { return __half2float(__ushort_as_half(b)); }
+
 // 16-bit K-major UMMA "interleaved" (no swizzle) layout: 8x8-element core matrices of 128 contiguous
 // bytes, K-adjacent cores contiguous (LBO = 128 B), 8-row groups Kp*16 B apart (SBO).
-void pack_umma_kmajor(const MlpLayer& L, int Np, int Kp, bool fp16, std::vector<uint16_t>& out) {
+// Element (n,k): k < L.in -> weight * wscale; k == L.in / L.in+1 -> hi / lo 16-bit halves of bias * bscale (the A
+// operand carries constant ones in those two columns); everything else zero.
+void pack_umma_kmajor(const MlpLayer& L, int Np, int Kp, bool fp16, double wscale, double bscale, std::vector<uint16_t>& out) {
   const size_t base = out.size();
   out.resize(base + (size_t)Np * Kp, 0);
+  auto enc = [&](float v) { return fp16 ? to_f16(v) : to_bf16(v); };
+  auto dec = [&](uint16_t b) { return fp16 ? from_f16(b) : from_bf16(b); };
   for (int n = 0; n < Np; ++n)
     for (int k = 0; k < Kp; ++k) {
-      const float v = (n < L.out && k < L.in) ? L.weight[(size_t)n * L.in + k] : 0.f;
+      uint16_t bits = 0;
+      if (n < L.out) {
+        if (k < L.in) bits = enc((float)((double)L.weight[(size_t)n * L.in + k] * wscale));
+        else if (k == L.in || k == L.in + 1) {
+          const float b = (float)((double)L.bias[n] * bscale);
+          const uint16_t hi = enc(b);
+          bits = (k == L.in) ? hi : enc(b - dec(hi));
+        }
+      }
       const size_t idx = ((size_t)(n / 8) * (Kp / 8) + (k / 8)) * 64 + (n % 8) * 8 + (k % 8);
-      out[base + idx] = fp16 ? to_f16(v) : to_bf16(v);
+      out[base + idx] = bits;
     }
 }
 
@@ -190,27 +202,29 @@ int upload_model(go2p_handle* h) {
   h->cc.foot_threshold = h->cfg.foot_threshold;
   h->cc.H = h->cfg.history;
 
-  // ---- tensor-core packing (narrow family: every hidden width 128, in <= 128, out <= 16)
-  bool narrow = dm.n_layers >= 2 && dm.in_dim <= 128 && dm.out_dim <= kTcOutPad;
+  // ---- tensor-core packing (narrow family: every hidden width 128, in + 2 <= 144, out <= 16).  The chain runs
+  // in the base-2 exponent domain (kernels_tc.cuh): an ELU layer's pre-activation and output are scaled by log2(e),
+  // the next layer's weights carry the inverse factor; biases ride in two extra K rows (hi/lo).
+  bool narrow = dm.n_layers >= 2 && dm.in_dim + 2 <= kTcHidden + kTcBiasK && dm.out_dim <= kTcOutPad;
   for (int l = 0; l + 1 < dm.n_layers; ++l) narrow = narrow && (m.layers[l].out == kTcHidden);
   if (narrow) {
-    h->k0p = round_up(dm.in_dim, 16);
+    h->k0p = round_up(dm.in_dim + 2, 16);
+    const double kLog2e = 1.4426950408889634074;
     std::vector<uint16_t> wb, wf;
-    std::vector<float> bias((size_t)dm.n_layers * 128, 0.f);
+    double in_scale = 1.0;
     for (int l = 0; l < dm.n_layers; ++l) {
-      const int Kp = l == 0 ? h->k0p : kTcHidden;
+      const int Kp = l == 0 ? h->k0p : kTcHidden + kTcBiasK;
       const int Np = l == dm.n_layers - 1 ? kTcOutPad : kTcHidden;
-      pack_umma_kmajor(m.layers[l], Np, Kp, false, wb);
-      pack_umma_kmajor(m.layers[l], Np, Kp, true, wf);
-      for (int o = 0; o < m.layers[l].out; ++o) bias[(size_t)l * 128 + o] = m.layers[l].bias[o];
+      const double out_scale = m.layers[l].has_elu ? kLog2e : 1.0;
+      pack_umma_kmajor(m.layers[l], Np, Kp, false, out_scale / in_scale, out_scale, wb);
+      pack_umma_kmajor(m.layers[l], Np, Kp, true, out_scale / in_scale, out_scale, wf);
+      in_scale = out_scale;
     }
     TcArgs probe{};
     probe.n_layers = dm.n_layers; probe.in_dim = dm.in_dim; probe.k0p = h->k0p;
     if (tc_smem_bytes(probe) <= 227 * 1024) {
       int rc;
-      if ((rc = dev_upload(h, wb, &h->d_wpack[0])) || (rc = dev_upload(h, wf, &h->d_wpack[1])) ||
-          (rc = dev_upload(h, bias, &h->d_bias_tc)))
-        return rc;
+      if ((rc = dev_upload(h, wb, &h->d_wpack[0])) || (rc = dev_upload(h, wf, &h->d_wpack[1]))) return rc;
       h->tc_ok = true;
     }
   }
@@ -399,17 +413,17 @@ int launch_fp32(go2p_handle* h, const float* d_obs, const int32_t* d_button0, fl
   return GO2P_OK;
 }
 
-template <bool kFp16, int kEpw>
+template <bool kFp16>
 int launch_tc_t(go2p_handle* h, const TcArgs& a, cudaStream_t st) {
   const size_t smem = tc_smem_bytes(a);
   static thread_local size_t set_for = 0;
   if (set_for != smem) {
-    CU_TRY(cudaFuncSetAttribute(tc_mlp_kernel<kFp16, kEpw>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(cudaFuncSetAttribute(tc_mlp_kernel<kFp16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     set_for = smem;
   }
   const long long tiles = (a.B + kTcTileM - 1) / kTcTileM;
   int grid = (int)std::min<long long>(tiles, h->sm_count - (h->resident ? 1 : 0));
-  tc_mlp_kernel<kFp16, kEpw><<<grid, (kTcCtrlWarps + 2 * kEpw) * 32, smem, st>>>(a);
+  tc_mlp_kernel<kFp16><<<grid, kTcThreads, smem, st>>>(a);
   h->last_launches++;
   CU_TRY(cudaGetLastError());
   return GO2P_OK;
@@ -423,15 +437,21 @@ int launch_tc(go2p_handle* h, const float* d_obs, const int32_t* d_button0, floa
   TcArgs a{};
   a.obs = d_obs; a.act = d_act; a.button0 = d_button0; a.qdes = d_qdes; a.B = B;
   a.wpack = h->d_wpack[fp16 ? 1 : 0];
-  a.bias = h->d_bias_tc;
   a.n_layers = h->dm.n_layers; a.in_dim = h->dm.in_dim; a.k0p = h->k0p; a.out_dim = h->dm.out_dim;
-  for (int l = 0; l < h->dm.n_layers; ++l) { a.has_elu[l] = h->dm.L[l].has_elu; a.alpha[l] = h->dm.L[l].alpha; }
+  for (int l = 0; l < h->dm.n_layers; ++l) {
+    a.has_elu[l] = h->dm.L[l].has_elu;
+    a.elu_c[l] = (float)((double)h->dm.L[l].alpha * 1.4426950408889634074);
+  }
+  a.out_scale = h->dm.L[h->dm.n_layers - 1].has_elu ? 0.69314718055994530942f : 1.0f;
   a.flags = flags;
   a.action_limit = h->cc.action_limit;
   a.action_scale = h->cc.action_scale;
   for (int i = 0; i < kDof; ++i) a.q0[i] = h->cc.q0[i];
-  if (h->tc_epw == 8) return fp16 ? launch_tc_t<true, 8>(h, a, st) : launch_tc_t<false, 8>(h, a, st);
-  return fp16 ? launch_tc_t<true, 4>(h, a, st) : launch_tc_t<false, 4>(h, a, st);
+  a.trace = nullptr;
+#ifdef GO2P_TC_TRACE
+  if (const char* e = std::getenv("GO2P_TC_TRACE_PTR")) a.trace = reinterpret_cast<unsigned long long*>(std::strtoull(e, nullptr, 0));
+#endif
+  return fp16 ? launch_tc_t<true>(h, a, st) : launch_tc_t<false>(h, a, st);
 }
 
 }  // namespace
@@ -505,8 +525,6 @@ int go2p_create(const char* onnx_path, const go2p_config* cfg_in, go2p_handle** 
   h->sm_count = prop.multiProcessorCount;
   h->cc_major = prop.major;
   h->cc_minor = prop.minor;
-  if (const char* e = std::getenv("GO2P_TC_DEBUG")) h->tc_debug = (uint32_t)std::strtoul(e, nullptr, 0);
-  if (const char* e = std::getenv("GO2P_TC_EPW")) h->tc_epw = std::atoi(e) == 8 ? 8 : 4;
   DeviceGuard g(h->device);
   int rc = upload_model(h);
   if (rc == GO2P_OK) {

@@ -11,6 +11,19 @@ namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a fully converged warp (elect.sync).  Unlike `lane == 0`, the compiler knows that exactly one
+// thread runs the guarded region, so warp-uniform instructions inside it (UTCHMMA, UBLKCP, ...) are emitted
+// straight instead of inside a per-active-thread "waterfall" loop (measured: ~150 -> ~64 cycles per MMA).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -68,7 +81,11 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {        // same wa
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+#ifdef GO2P_EXP_NOWAITST
+__device__ __forceinline__ void tc_wait_st() {}   // timing experiment only: unsafe ordering
+#else
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+#endif
 
 // ------------------------------------------------------------------ tcgen05: descriptors
 // Shared-memory matrix descriptor, K-major operand, SWIZZLE_NONE ("interleaved" 8x16B core matrices):
@@ -125,6 +142,9 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[16]) {
       : GO2P_R4(v, 0), GO2P_R4(v, 4), GO2P_R4(v, 8), GO2P_R4(v, 12)
       : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : GO2P_R4(v, 0) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
@@ -147,7 +167,21 @@ __device__ __forceinline__ uint32_t pack_f16_sat(float lo, float hi) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// per 16-bit half: neg where z < 0 (ONNX Elu: -0.0 and NaN take the pass-through side), else z
+__device__ __forceinline__ uint32_t select_neg_f16x2(uint32_t z, uint32_t neg) {
+  uint32_t m;
+  asm("set.lt.u32.f16x2 %0, %1, %2;" : "=r"(m) : "r"(z), "r"(0u));
+  return (neg & m) | (z & ~m);
+}
+__device__ __forceinline__ uint32_t select_neg_bf16x2(uint32_t z, uint32_t neg) {
+  uint32_t m;
+  asm("set.lt.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(z), "r"(0u));
+  return (neg & m) | (z & ~m);
+}
 __device__ __forceinline__ float ex2_approx(float x) {
+#ifdef GO2P_EXP_NOMUFU
+  return x + 1.0f;   // timing experiment only: wrong numerics, no MUFU
+#endif
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
