@@ -269,10 +269,10 @@ def main():
                                  "mode": "resident kernel, host-mapped mailbox, fused A1-A6+A7+A9+A11"}
     if rank == 0 and world == 1 and not args.no_cpu:
         r0, _, thr = cpu_reference_rate(32768, 1, 1)
-        sample_rows = int(min(4_194_304, max(65536, r0 * 12)))          # ~12 s of CPU work
-        rate, dtc, thr = cpu_reference_rate(sample_rows, 1, 0)
+        passes = int(max(1, min(64, round(r0 * 12 / rows))))          # ~12 s of CPU work over the same rows
+        rate, dtc, thr = cpu_reference_rate(rows, passes, 0)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": thr, "kind": "port",
-                                "sample": f"{sample_rows} rows of the same N(0,1) workload in {dtc:.1f} s; C restatement "
+                                "sample": f"{passes} passes over {rows} rows of the same N(0,1) workload in {dtc:.1f} s; C restatement "
                                           "(oracle/oracle_mlp.c), batch-1 semantics per row, OpenMP over all host cores; "
                                           "ORT CPU EP itself is not installable here"}
     pb.close()

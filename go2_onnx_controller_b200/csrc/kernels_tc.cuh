@@ -33,7 +33,8 @@ constexpr int kTcTileM = 128;
 constexpr int kTcHidden = 128;     // every hidden width handled by this kernel
 constexpr int kTcOutPad = 16;      // last layer N padded to 16 (smallest UMMA N at M=128)
 constexpr int kTcBiasK = 16;       // extra K block carrying the two constant-one columns (bias hi / lo)
-constexpr int kTcWorkers = 16;     // warps 0..15: 4 TMEM lane quarters (warp % 4) x 4 column blocks, shared by both slots
+constexpr int kTcWorkers = 16;     // warps 0..7 serve slot 0, 8..15 slot 1: 4 TMEM lane quarters (warp % 4) x 2 column halves
+constexpr int kTcPool = 8;         // worker warps per slot
 constexpr int kTcProducerWarp = 16;  // bulk-copy producer
 constexpr int kTcMmaWarp = 17;       // MMA issuer + TMEM owner
 constexpr int kTcThreads = (kTcWorkers + 2) * 32;
@@ -140,8 +141,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const TcArgs a) {
     if (lane == 0) {
       for (int s = 0; s < 2; ++s) {
         ptx::mbar_init(&obs_full[s], 1);
-        ptx::mbar_init(&obs_empty[s], kTcWorkers);
-        ptx::mbar_init(&a_ready[s], kTcWorkers);
+        ptx::mbar_init(&obs_empty[s], kTcPool);
+        ptx::mbar_init(&a_ready[s], kTcPool);
         ptx::mbar_init(&acc_full[s], 1);
       }
       ptx::fence_mbar_init();
@@ -181,23 +182,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const TcArgs a) {
     }
   } else if (warp == kTcMmaWarp) {
     // ================= MMA issuer: one elected thread drives the tensor core =================
+    // The two slots are served in whatever order their A operands become ready (non-blocking polls), so the
+    // pools drift into anti-phase: one computes its ELU while the tensor core runs the other's layer.
     const uint32_t fmt = kFp16 ? ptx::FMT_F16 : ptx::FMT_BF16;
-    uint32_t par[2] = {0u, 0u};
     const uint32_t w_base = ptx::smem_u32(w_smem);
-    for (int pair = 0; pair * 2 < n_local; ++pair) {
-      uint32_t w_off = 0;
-      for (int l = 0; l < a.n_layers; ++l) {
-        const int kp = tc_layer_kp(a, l), nl = tc_layer_n(a, l);
-        const uint32_t idesc = ptx::make_idesc(fmt, kTcTileM, (uint32_t)nl);
-        // K step of 16 elements = two 8x16B core matrices along K (LBO = 128 B apart); 8-row groups are
-        // kp*16 B apart (SBO); consecutive K steps are 256 B apart (+16 in the descriptor's address field)
-        const uint64_t bdesc0 = ptx::make_smem_desc_nosw(w_base + w_off, 128u, (uint32_t)kp * 16u);
-        const int ksteps = kp / 16;
-        for (int s = 0; s < 2; ++s) {
-          if (pair * 2 + s >= n_local) continue;
-          ptx::mbar_wait(&a_ready[s], par[s]);
+    uint32_t par[2] = {0u, 0u};
+    int lay[2] = {0, 0};
+    uint32_t woff[2] = {0u, 0u};
+    int left[2] = {(n_local + 1) / 2, n_local / 2};       // tiles still to issue per slot
+    int s = 0;
+    while (left[0] > 0 || left[1] > 0) {
+      if (left[s] > 0) {
+        const bool ready = __all_sync(0xffffffffu, ptx::mbar_try_wait(&a_ready[s], par[s]));
+        if (ready) {
           par[s] ^= 1u;
           ptx::tc_fence_after();
+          const int l = lay[s];
+          const int kp = tc_layer_kp(a, l), nl = tc_layer_n(a, l);
+          const uint32_t idesc = ptx::make_idesc(fmt, kTcTileM, (uint32_t)nl);
+          // K step of 16 elements = two 8x16B core matrices along K (LBO = 128 B apart); 8-row groups are
+          // kp*16 B apart (SBO); consecutive K steps are 256 B apart (+16 in the descriptor's address field)
+          const uint64_t bdesc0 = ptx::make_smem_desc_nosw(w_base + woff[s], 128u, (uint32_t)kp * 16u);
+          const int ksteps = kp / 16;
           const uint32_t d_t = tmem_base + (uint32_t)s * kTcSlotCols;
           const uint32_t a_t = d_t + 128u;
           if (ptx::elect_one_sync()) {
@@ -209,142 +215,134 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const TcArgs a) {
             TC_TRACE(0x300u | (uint32_t)(l << 4) | (uint32_t)s);
           }
           __syncwarp();
+          woff[s] += (uint32_t)(kp * nl * 2);
+          if (++lay[s] == a.n_layers) { lay[s] = 0; woff[s] = 0u; --left[s]; }
         }
-        w_off += (uint32_t)(kp * nl * 2);
       }
+      s ^= 1;
     }
   } else {
-    // ================= worker warps: one pool of 16 warps walks the job list of both slots =================
-    // job order == MMA issue order: conv(s0) conv(s1) | E(l,s0) E(l,s1) for every hidden layer | out(s0) out(s1).
-    // While the pool works on one slot the tensor core runs the other slot's next layer, so the MUFU pipe has
-    // 4 warps per scheduler feeding it.  The TMEM load of the next job is issued before the tail (store, fences,
-    // barrier arrive) of the current one, so job boundaries do not drain the pipe.
+    // ================= worker warps: one pool of 8 warps per slot =================
+    // pool = 4 TMEM lane quarters x 2 column halves; every warp owns 64 columns of each hidden layer (two
+    // 32-column chunks, both loaded up front so the second load and the first store overlap the arithmetic).
+    const int s = warp >> 3;                 // slot == pool
     const int quarter = warp & 3;            // TMEM lane quarter this warp may touch (== warp % 4)
-    const int cb = warp >> 2;                // 32-column block of every hidden layer this warp owns (0..3)
+    const int half = (warp >> 2) & 1;        // column half
     const uint32_t lane_addr = ((uint32_t)(quarter * 32)) << 16;
+    const uint32_t acc_t = tmem_base + (uint32_t)s * kTcSlotCols + lane_addr;
+    const uint32_t a_t = acc_t + 128u;
     const int m = quarter * 32 + lane;       // row inside the tile
     const uint32_t one2 = kFp16 ? 0x3C003C00u : 0x3F803F80u;   // packed (1.0, 1.0)
     const int L = a.n_layers - 1;            // index of the output layer
     const bool out12 = a.out_dim == 12;
+    const int n8 = a.k0p / 16;               // layer-0 A operand: chunks of 8 packed columns (16 elements)
+    const bool even = (a.in_dim & 1) == 0;
 
     // constant-one columns of the hidden-layer A operand (K = 128,129), zeros up to K = 143: written once
-    if (cb == 0) {
+    if (half == 0) {
       const uint32_t ones[8] = {one2, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-      for (int s = 0; s < 2; ++s) ptx::tmem_st_x8(tmem_base + (uint32_t)s * kTcSlotCols + lane_addr + 128u + (uint32_t)(kTcHidden / 2), ones);
+      ptx::tmem_st_x8(a_t + (uint32_t)(kTcHidden / 2), ones);
       ptx::tc_wait_st();
     }
 
-    uint32_t par_acc[2] = {0u, 0u};
-    const int n8 = a.k0p / 16;               // layer-0 A operand: chunks of 8 packed columns (16 elements)
-    const bool even = (a.in_dim & 1) == 0;
-    uint32_t v[32], p[16];
+    uint32_t par_acc = 0u;
+    int n = 0;
+    for (int i = s; i < n_local; i += 2, ++n) {
+      const long long row0 = (blockIdx.x + (long long)i * gridDim.x) * kTcTileM;
+      const int valid = (int)min((long long)kTcTileM, a.B - row0);
 
-    // issue the TMEM load of job (l, s): a hidden layer's 32 columns, or this warp's share of the output layer
-    auto issue_load = [&](int l, int s) {
-      const uint32_t acc_t = tmem_base + (uint32_t)s * kTcSlotCols + lane_addr;
-      ptx::mbar_wait(&acc_full[s], par_acc[s]);
-      par_acc[s] ^= 1u;
-      ptx::tc_fence_after();
-      if (l < L) ptx::tmem_ld_x32(acc_t + (uint32_t)(cb * 32), v);
-      else if (out12) { if (cb < 3) ptx::tmem_ld_x4(acc_t + (uint32_t)(cb * 4), reinterpret_cast<uint32_t(&)[4]>(v)); }
-      else if (cb == 0) ptx::tmem_ld_x16(acc_t, reinterpret_cast<uint32_t(&)[16]>(v));
-    };
-
-    for (int pair = 0; pair * 2 < n_local; ++pair) {
-      const int ns = min(2, n_local - pair * 2);
-      // ---- conv(s): fp32 observation rows -> 16-bit layer-0 A operand in TMEM, constant ones at K = in_dim, in_dim+1
-      for (int s = 0; s < ns; ++s) {
-        const long long row0 = (blockIdx.x + (long long)(pair * 2 + s) * gridDim.x) * kTcTileM;
-        const int valid = (int)min((long long)kTcTileM, a.B - row0);
-        const uint32_t a_t = tmem_base + (uint32_t)s * kTcSlotCols + lane_addr + 128u;
-        ptx::mbar_wait(&obs_full[s], (uint32_t)(pair & 1));
-        TC_TRACE(0x400u | (uint32_t)s);
-        if (valid == kTcTileM && even) {
-          // full tile in shared memory, rows 8-byte aligned: vector loads, uniform per-pair classification
-          const float2* r2 = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(stage0 + s * stage_bytes) + (size_t)m * a.in_dim);
+      // ---- conv: fp32 observation rows -> 16-bit layer-0 A operand in TMEM, constant ones at K = in_dim, in_dim+1
+      ptx::mbar_wait(&obs_full[s], (uint32_t)(n & 1));
+      TC_TRACE(0x400u | (uint32_t)s);
+      if (valid == kTcTileM && even) {
+        // full tile in shared memory, rows 8-byte aligned: vector loads, uniform per-pair classification
+        const float2* r2 = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(stage0 + s * stage_bytes) + (size_t)m * a.in_dim);
 #pragma unroll
-          for (int it = 0; it < 3; ++it) {
-            const int c8 = cb + 4 * it;
-            if (c8 < n8) {
-              uint32_t q[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int k = c8 * 16 + 2 * j;
-                if (k < a.in_dim) { const float2 t = r2[k >> 1]; q[j] = kFp16 ? ptx::pack_f16_sat(t.x, t.y) : ptx::pack_bf16(t.x, t.y); }
-                else q[j] = (k == a.in_dim) ? one2 : 0u;
-              }
-              ptx::tmem_st_x8(a_t + (uint32_t)c8 * 8u, q);
-            }
-          }
-        } else {
-          // ragged last tile (read straight from global memory) or odd input width: scalar path
-          const float* rowp = (valid == kTcTileM) ? reinterpret_cast<const float*>(stage0 + s * stage_bytes) + (size_t)m * a.in_dim
-                                                  : a.obs + (row0 + m) * a.in_dim;
-          const bool live = m < valid;
-          for (int c8 = cb; c8 < n8; c8 += 4) {
+        for (int it = 0; it < 5; ++it) {
+          const int c8 = half + 2 * it;
+          if (c8 < n8) {
             uint32_t q[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int k = c8 * 16 + 2 * j;
-              float lo = 0.f, hi = 0.f;
-              if (k < a.in_dim) { if (live) lo = rowp[k]; } else if (k <= a.in_dim + 1) lo = 1.f;
-              if (k + 1 < a.in_dim) { if (live) hi = rowp[k + 1]; } else if (k + 1 <= a.in_dim + 1) hi = 1.f;
-              q[j] = kFp16 ? ptx::pack_f16_sat(lo, hi) : ptx::pack_bf16(lo, hi);
+              if (k < a.in_dim) { const float2 t = r2[k >> 1]; q[j] = kFp16 ? ptx::pack_f16_sat(t.x, t.y) : ptx::pack_bf16(t.x, t.y); }
+              else q[j] = (k == a.in_dim) ? one2 : 0u;
             }
             ptx::tmem_st_x8(a_t + (uint32_t)c8 * 8u, q);
           }
         }
-        ptx::tc_wait_st();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) { ptx::mbar_arrive(&obs_empty[s]); ptx::mbar_arrive(&a_ready[s]); }
-        TC_TRACE(0x500u | (uint32_t)s);
+      } else {
+        // ragged last tile (read straight from global memory) or odd input width: scalar path
+        const float* rowp = (valid == kTcTileM) ? reinterpret_cast<const float*>(stage0 + s * stage_bytes) + (size_t)m * a.in_dim
+                                                : a.obs + (row0 + m) * a.in_dim;
+        const bool live = m < valid;
+        for (int c8 = half; c8 < n8; c8 += 2) {
+          uint32_t q[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k = c8 * 16 + 2 * j;
+            float lo = 0.f, hi = 0.f;
+            if (k < a.in_dim) { if (live) lo = rowp[k]; } else if (k <= a.in_dim + 1) lo = 1.f;
+            if (k + 1 < a.in_dim) { if (live) hi = rowp[k + 1]; } else if (k + 1 <= a.in_dim + 1) hi = 1.f;
+            q[j] = kFp16 ? ptx::pack_f16_sat(lo, hi) : ptx::pack_bf16(lo, hi);
+          }
+          ptx::tmem_st_x8(a_t + (uint32_t)c8 * 8u, q);
+        }
       }
+      ptx::tc_wait_st();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { ptx::mbar_arrive(&obs_empty[s]); ptx::mbar_arrive(&a_ready[s]); }
+      TC_TRACE(0x500u | (uint32_t)s);
 
-      // ---- E(l,s): accumulator -> ELU -> 16-bit A operand of the next layer (32 columns per warp)
-      bool loaded = false;
+      // ---- hidden layers: accumulator -> ELU -> 16-bit A operand of the next layer (64 columns per warp)
       for (int l = 0; l < L; ++l) {
         const bool he = a.has_elu[l] != 0;
         const float c = a.elu_c[l];
-        for (int s = 0; s < ns; ++s) {
-          if (!loaded) issue_load(l, s);
-          ptx::tc_wait_ld();
-          TC_TRACE(0x600u | (uint32_t)(l << 4) | (uint32_t)s);
-          elu_pack32<kFp16>(v, he, c, p);
-          TC_TRACE(0xA00u | (uint32_t)(l << 4) | (uint32_t)s);
-          // v is dead now: with two slots in flight the next job belongs to the other slot, whose MMA was issued
-          // a whole job ago and depends on nothing this job still has to signal -> fetch its accumulator early
-          loaded = false;
-          if (ns == 2) { if (s == 0) issue_load(l, 1); else issue_load(l + 1, 0); loaded = true; }
-          TC_TRACE(0xB00u | (uint32_t)(l << 4) | (uint32_t)s);
-          ptx::tmem_st_x16(tmem_base + (uint32_t)s * kTcSlotCols + lane_addr + 128u + (uint32_t)(cb * 16), p);
-          ptx::tc_wait_st();
-          TC_TRACE(0xC00u | (uint32_t)(l << 4) | (uint32_t)s);
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&a_ready[s]);
-          TC_TRACE(0x700u | (uint32_t)(l << 4) | (uint32_t)s);
-        }
+        uint32_t v0[32], v1[32], p0[16], p1[16];
+        ptx::mbar_wait(&acc_full[s], par_acc);
+        par_acc ^= 1u;
+        ptx::tc_fence_after();
+        ptx::tmem_ld_x32(acc_t + (uint32_t)(half * 64), v0);
+        ptx::tmem_ld_x32(acc_t + (uint32_t)(half * 64 + 32), v1);
+        ptx::tc_wait_ld();
+        TC_TRACE(0x600u | (uint32_t)(l << 4) | (uint32_t)s);
+        elu_pack32<kFp16>(v0, he, c, p0);
+        ptx::tmem_st_x16(a_t + (uint32_t)(half * 32), p0);
+        elu_pack32<kFp16>(v1, he, c, p1);
+        ptx::tmem_st_x16(a_t + (uint32_t)(half * 32 + 16), p1);
+        TC_TRACE(0xA00u | (uint32_t)(l << 4) | (uint32_t)s);
+        ptx::tc_wait_st();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&a_ready[s]);
+        TC_TRACE(0x700u | (uint32_t)(l << 4) | (uint32_t)s);
       }
 
-      // ---- out(s) (bias already inside the accumulator): (+ELU) (+clamp/mask) (+q_des) -> global
-      for (int s = 0; s < ns; ++s) {
-        const long long row0 = (blockIdx.x + (long long)(pair * 2 + s) * gridDim.x) * kTcTileM;
-        const int valid = (int)min((long long)kTcTileM, a.B - row0);
-        if (!loaded) issue_load(L, s);
+      // ---- output layer (bias already inside the accumulator): (+ELU) (+clamp/mask) (+q_des) -> global
+      // 12 outputs: half 0 stores columns 0..7, half 1 columns 8..11; other widths: half 0 does all 16 columns
+      ptx::mbar_wait(&acc_full[s], par_acc);
+      par_acc ^= 1u;
+      ptx::tc_fence_after();
+      TC_TRACE(0x800u | (uint32_t)s);
+      {
+        uint32_t v[16];
+        const int col0 = out12 ? half * 8 : 0;
+        const int nv = out12 ? (half == 0 ? 8 : 4) : 16;
+        const bool active = out12 || half == 0;
+        if (active) {
+          if (nv == 16) ptx::tmem_ld_x16(acc_t, v);
+          else if (nv == 8) ptx::tmem_ld_x8(acc_t, reinterpret_cast<uint32_t(&)[8]>(v));
+          else ptx::tmem_ld_x4(acc_t + 8u, reinterpret_cast<uint32_t(&)[4]>(v));
+        }
         ptx::tc_wait_ld();
-        TC_TRACE(0x800u | (uint32_t)s);
         float o[16];
-        const int nv = out12 ? 4 : 16;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float x = __uint_as_float(v[j]);
           if (a.has_elu[L]) x = ((x < 0.f) ? fmaf(ptx::ex2_approx(x), a.elu_c[L], -a.elu_c[L]) : x) * a.out_scale;
           o[j] = x;
         }
-        loaded = false;
-        if (ns == 2 && s == 0) { issue_load(L, 1); loaded = true; }   // o[] holds what this job needs
-        const bool active = out12 ? (cb < 3) : (cb == 0);
         if (active && m < valid) {
           const long long row = row0 + m;
           if (a.flags & 1u) {
@@ -352,22 +350,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const TcArgs a) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) if (j < nv) o[j] = clamp_mask(o[j], a.action_limit, b0);
           }
-          float* dst = a.act + row * a.out_dim;
+          float* dst = a.act + row * a.out_dim + col0;
           if (out12) {
-            reinterpret_cast<float4*>(dst)[cb] = make_float4(o[0], o[1], o[2], o[3]);
+            reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
+            if (half == 0) reinterpret_cast<float4*>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
             if ((a.flags & 2u) && a.qdes) {
-              double2* q2 = reinterpret_cast<double2*>(a.qdes + row * kDof + cb * 4);
-              q2[0] = make_double2(joint_target(o[0], a.q0[cb * 4 + 0], a.action_scale), joint_target(o[1], a.q0[cb * 4 + 1], a.action_scale));
-              q2[1] = make_double2(joint_target(o[2], a.q0[cb * 4 + 2], a.action_scale), joint_target(o[3], a.q0[cb * 4 + 3], a.action_scale));
+              double2* q2 = reinterpret_cast<double2*>(a.qdes + row * kDof + col0);
+#pragma unroll
+              for (int j = 0; j < 8; j += 2)
+                if (j < nv) q2[j >> 1] = make_double2(joint_target(o[j], a.q0[col0 + j], a.action_scale), joint_target(o[j + 1], a.q0[col0 + j + 1], a.action_scale));
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) if (j < a.out_dim) dst[j] = o[j];
           }
         }
-        ptx::tc_fence_before();
-        TC_TRACE(0x900u | (uint32_t)s);
       }
+      ptx::tc_fence_before();
+      TC_TRACE(0x900u | (uint32_t)s);
     }
   }
 

@@ -1,7 +1,6 @@
 """TEST INFRASTRUCTURE -- ctypes binding of oracle/_build/liboracle.so (the plain-C
-restatement) and of oracle/_ref/libref_controller.so (the reference's own
-controller.cpp / onnx_actor.cpp compiled against stubs).  Only tests/, smoke() and
-bench.py's cpu_baseline / --impl reference legs may import this."""
+restatement; "parity unpinned", see oracle.h).  Only tests/, smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this."""
 from __future__ import annotations
 
 import ctypes as C
@@ -12,7 +11,6 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_build", "liboracle.so")
-REF_LIB_PATH = os.path.join(HERE, "_ref", "libref_controller.so")
 
 ORC_MAX_LAYERS = 16
 ORC_MAX_HIST = 8
@@ -63,10 +61,9 @@ class StepOut(C.Structure):
 
 
 def build(force: bool = False) -> None:
-    """Compile the C restatement (and oracle/_ref when the reference tree is present)."""
+    """Compile the C restatement."""
     if force or not os.path.exists(LIB_PATH):
         subprocess.run(["make", "-C", HERE, LIB_PATH], check=True, capture_output=True)
-    subprocess.run(["make", "-C", HERE, "ref"], check=False, capture_output=True)
 
 
 _lib = None

@@ -2,9 +2,12 @@
  * path.  Linked / loaded only by tests/, __graft_entry__.smoke() and the
  * cpu_baseline / --impl reference legs of bench.py.  Never by the product.
  *
- * PARITY STATUS: A7 "parity unpinned" (ONNX Runtime 1.20.1 binary absent, the
- * reference holds no golden vector); A1-A6/A9-A11 pinned against the
- * reference's controller.cpp built into oracle/_ref (see oracle/Makefile).
+ * PARITY STATUS: "parity unpinned" -- the ONNX Runtime 1.20.1 binary that holds
+ * A7's arithmetic is absent, the reference holds no golden vector, and
+ * controller.cpp cannot be compiled here (ROS 2 / Eigen absent), so no
+ * oracle/_ref exists.  Pinned instead by three independent restatements
+ * (numpy fp64, this C code, torch-CPU fp64) that agree to 2e-15 and by the
+ * known-answer vectors of SURVEY.md Appendix D (tests/test_oracle.py).
  */
 #ifndef GO2_ORACLE_H
 #define GO2_ORACLE_H
