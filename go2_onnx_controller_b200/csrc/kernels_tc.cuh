@@ -10,10 +10,14 @@
 //   * observations stream in as 1-D bulk async copies (TMA engine) of whole 128-row slabs
 //     ([128,in] fp32 is contiguous; its 392-byte row pitch rules out a 2-D tensor map) into a
 //     2-stage shared-memory ring guarded by mbarriers;
-//   * two 128-row tiles are in flight per CTA ("slots").  Each slot owns 128 TMEM columns of fp32
-//     accumulator and 72 columns of 16-bit A operand.  The activation of layer l never leaves the SM:
-//     epilogue warps read the accumulator with tcgen05.ld, apply ELU, pack to 16 bit and write it back
-//     to TMEM with tcgen05.st, where the next layer's tcgen05.mma reads it as its A operand (TS form);
+//   * two 128-row tiles are in flight per CTA ("slots").  Each slot owns two 128-column TMEM buffers used
+//     in ping-pong: layer l accumulates into one buffer; the epilogue warps read that accumulator with
+//     tcgen05.ld, apply ELU, pack to 16 bit and write the result back IN PLACE (the first 16 columns of
+//     every 32-column block) with tcgen05.st, where the next layer's tcgen05.mma reads it as its A
+//     operand (TS form) while accumulating into the other buffer.  The activation never leaves the SM;
+//   * A-operand readiness is tracked per 32-column block (one mbarrier each), so the next layer's K steps
+//     are issued while the epilogue is still working on later blocks: the MMA trails the epilogue instead
+//     of starting after it;
 //   * the bias rides inside the MMA: every A operand carries two constant 1.0 columns and the weight
 //     matrix two extra K rows holding hi/lo halves of the bias, so the epilogue has no bias add;
 //   * the chain is evaluated in the base-2 exponent domain: layer l produces z' = log2(e)*z, the ELU is
@@ -35,10 +39,10 @@ constexpr int kTcOutPad = 16;      // last layer N padded to 16 (smallest UMMA N
 constexpr int kTcBiasK = 16;       // extra K block carrying the two constant-one columns (bias hi / lo)
 constexpr int kTcWorkers = 16;     // warps 0..7 serve slot 0, 8..15 slot 1: 4 TMEM lane quarters (warp % 4) x 2 column halves
 constexpr int kTcPool = 8;         // worker warps per slot
-constexpr int kTcProducerWarp = 16;  // bulk-copy producer
-constexpr int kTcMmaWarp = 17;       // MMA issuer + TMEM owner
+constexpr int kTcCtrlWarp0 = 16;      // warps 16,17: per-slot control warp = bulk-copy producer + MMA issuer; warp 16 owns TMEM
 constexpr int kTcThreads = (kTcWorkers + 2) * 32;
-constexpr int kTcSlotCols = 256;   // TMEM columns per slot: [0,128) accumulator, [128,200) A operand
+constexpr int kTcSlotCols = 256;   // TMEM columns per slot: two 128-column ping-pong buffers
+constexpr int kTcBlocks = 4;       // 32-column blocks per buffer, each with its own A-ready barrier
 
 struct TcArgs {
   const float* obs;          // [B, in_dim]
@@ -88,6 +92,25 @@ __host__ __device__ inline size_t tc_smem_bytes(const TcArgs& a) { return tc_wei
 
 // ELU in the base-2 domain on 32 accumulator columns -> 16 words of packed 16-bit operands.
 //   e = 2^z' (MUFU), f = c*e - c (FFMA), result = z' < 0 ? f : z' selected on the packed pair.
+// same on 8 accumulator columns -> 4 packed words (the rolled epilogue loop works in groups of 8 columns)
+template <bool kFp16>
+__device__ __forceinline__ void elu_pack8(const uint32_t (&v)[8], bool has_elu, float c, uint32_t (&p)[4]) {
+  const float nc = -c;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float z0 = __uint_as_float(v[2 * j]), z1 = __uint_as_float(v[2 * j + 1]);
+    const uint32_t zp = kFp16 ? ptx::pack_f16_sat(z0, z1) : ptx::pack_bf16(z0, z1);
+    if (has_elu) {
+      const float f0 = fmaf(ptx::ex2_approx(z0), c, nc);
+      const float f1 = fmaf(ptx::ex2_approx(z1), c, nc);
+      const uint32_t fp = kFp16 ? ptx::pack_f16_sat(f0, f1) : ptx::pack_bf16(f0, f1);
+      p[j] = kFp16 ? ptx::select_neg_f16x2(zp, fp) : ptx::select_neg_bf16x2(zp, fp);
+    } else {
+      p[j] = zp;
+    }
+  }
+}
+
 template <bool kFp16>
 __device__ __forceinline__ void elu_pack32(const uint32_t (&v)[32], bool has_elu, float c, uint32_t (&p)[16]) {
   if (has_elu) {
@@ -114,6 +137,49 @@ __device__ __forceinline__ void elu_pack32(const uint32_t (&v)[32], bool has_elu
   }
 }
 
+
+// ---- cold paths, kept out of line so the steady-state loop of the kernel stays small in the instruction cache
+// (measured: with everything inlined the kernel was 40 KB of SASS, above the 32 KB L1.5 instruction cache, and
+// every phase of the 18-warp pipeline paid instruction-fetch misses: ~1000 cycles for a backward branch)
+
+// layer-0 A operand of one row for a ragged last tile (read from global memory) or an odd input width
+template <bool kFp16>
+__device__ __noinline__ void tc_conv_slow(const TcArgs& a, const float* rowp, bool live, int c8_lo, int c8_hi, uint32_t a0_t) {
+  for (int c8 = c8_lo; c8 < c8_hi; ++c8) {
+    uint32_t q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = c8 * 16 + 2 * j;
+      float lo = 0.f, hi = 0.f;
+      if (k < a.in_dim) { if (live) lo = rowp[k]; } else if (k <= a.in_dim + 1) lo = 1.f;
+      if (k + 1 < a.in_dim) { if (live) hi = rowp[k + 1]; } else if (k + 1 <= a.in_dim + 1) hi = 1.f;
+      q[j] = kFp16 ? ptx::pack_f16_sat(lo, hi) : ptx::pack_bf16(lo, hi);
+    }
+    ptx::tmem_st_x8(a0_t + (uint32_t)(32 * (c8 >> 1) + 8 * (c8 & 1)), q);
+  }
+}
+
+// output epilogue for anything but the plain 12-output, no-activation case: one warp per lane quarter (half 0)
+__device__ __noinline__ void tc_out_generic(const TcArgs& a, uint32_t o_t, long long row, bool live) {
+  uint32_t v[16];
+  ptx::tmem_ld_x16(o_t, v);
+  ptx::tc_wait_ld();
+  if (!live) return;
+  const int L = a.n_layers - 1;
+  const int b0 = (a.flags & 1u) && a.button0 ? a.button0[row] : 0;
+  float* dst = a.act + row * a.out_dim;
+#pragma unroll 1
+  for (int j = 0; j < a.out_dim; ++j) {
+    float x = __uint_as_float(v[0]);
+#pragma unroll
+    for (int q = 1; q < 16; ++q) if (q == j) x = __uint_as_float(v[q]);
+    if (a.has_elu[L]) x = ((x < 0.f) ? fmaf(ptx::ex2_approx(x), a.elu_c[L], -a.elu_c[L]) : x) * a.out_scale;
+    if (a.flags & 1u) x = clamp_mask(x, a.action_limit, b0);
+    dst[j] = x;
+    if ((a.flags & 2u) && a.qdes && j < kDof) a.qdes[row * kDof + j] = joint_target(x, a.q0[j], a.action_scale);
+  }
+}
+
 template <bool kFp16>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const TcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -126,9 +192,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const TcArgs a) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + 2 * stage_bytes);
   uint64_t* obs_full = bars;        // [2]
   uint64_t* obs_empty = bars + 2;   // [2]
-  uint64_t* a_ready = bars + 4;     // [2]
-  uint64_t* acc_full = bars + 6;    // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* acc_full = bars + 4;    // [2]
+  uint64_t* a_blk = bars + 6;       // [2][4]  A operand of the next layer ready, per 32-column block
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
 
   // ---- one-time setup: weights -> smem, barriers, TMEM
   {
@@ -137,13 +203,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const TcArgs a) {
     const int n16 = (int)(wbytes >> 4);
     for (int i = tid; i < n16; i += kTcThreads) dst[i] = src[i];
   }
-  if (warp == kTcMmaWarp) {
+  if (warp == kTcCtrlWarp0) {
     if (lane == 0) {
       for (int s = 0; s < 2; ++s) {
         ptx::mbar_init(&obs_full[s], 1);
-        ptx::mbar_init(&obs_empty[s], kTcPool);
-        ptx::mbar_init(&a_ready[s], kTcPool);
         ptx::mbar_init(&acc_full[s], 1);
+        for (int b = 0; b < kTcBlocks; ++b) ptx::mbar_init(&a_blk[s * kTcBlocks + b], 4);   // 4 lane quarters
       }
       ptx::fence_mbar_init();
     }
@@ -161,211 +226,222 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const TcArgs a) {
   const uint32_t tile_bytes = (uint32_t)(kTcTileM * a.in_dim * 4);
   TC_TRACE_INIT();
 
-  if (warp == kTcProducerWarp) {
-    // ================= producer: bulk async copies of observation slabs =================
-    // (the whole warp walks the loop converged; one elected lane issues)
-    for (int i = 0; i < n_local; ++i) {
-      const int s = i & 1, n = i >> 1;
-      ptx::mbar_wait(&obs_empty[s], (uint32_t)((n & 1) ^ 1));
-      const long long tile = blockIdx.x + (long long)i * gridDim.x;
-      const long long row0 = tile * kTcTileM;
-      if (ptx::elect_one_sync()) {
-        if (a.B - row0 >= kTcTileM) {
-          TC_TRACE(0x100u | (uint32_t)s);
-          ptx::mbar_arrive_expect_tx(&obs_full[s], tile_bytes);
-          ptx::bulk_g2s(stage0 + s * stage_bytes, a.obs + row0 * a.in_dim, tile_bytes, &obs_full[s]);
-        } else {
-          ptx::mbar_arrive(&obs_full[s]);   // ragged last tile: consumers read global memory directly
-        }
-      }
-      __syncwarp();
-    }
-  } else if (warp == kTcMmaWarp) {
-    // ================= MMA issuer: one elected thread drives the tensor core =================
-    // The two slots are served in whatever order their A operands become ready (non-blocking polls), so the
-    // pools drift into anti-phase: one computes its ELU while the tensor core runs the other's layer.
+  if (warp >= kTcCtrlWarp0) {
+    // ================= control warp of slot s: bulk-copy producer + MMA issuer =================
+    // One warp per slot walks that slot's tiles and layers and blocks on the A-ready barrier of each 32-column
+    // block in the fixed order 0,2,1,3 (the order the pool finishes them), issuing that block's K steps at once:
+    // the MMA trails the epilogue, and the fixed order keeps the fp32 accumulation order (every output bit)
+    // independent of timing.  Layer 0 waits for all four blocks (its first K step overwrites the buffer the
+    // previous tile's output epilogue reads, and a warp signals its blocks only after that read); at that point
+    // the observation stage of this slot is free as well, so the next tile's bulk copy is issued right there.
+    const int s = warp - kTcCtrlWarp0;
     const uint32_t fmt = kFp16 ? ptx::FMT_F16 : ptx::FMT_BF16;
     const uint32_t w_base = ptx::smem_u32(w_smem);
-    uint32_t par[2] = {0u, 0u};
-    int lay[2] = {0, 0};
-    uint32_t woff[2] = {0u, 0u};
-    int left[2] = {(n_local + 1) / 2, n_local / 2};       // tiles still to issue per slot
-    int s = 0;
-    while (left[0] > 0 || left[1] > 0) {
-      if (left[s] > 0) {
-        const bool ready = __all_sync(0xffffffffu, ptx::mbar_try_wait(&a_ready[s], par[s]));
-        if (ready) {
-          par[s] ^= 1u;
+    uint64_t* blk = &a_blk[s * kTcBlocks];
+    uint8_t* stage = stage0 + s * stage_bytes;
+    uint32_t par = 0u;                       // all four block barriers of a slot advance one phase per layer
+    auto load_tile = [&](int i) {            // i = CTA-local tile index (slot s owns i = s, s+2, ...)
+      const long long row0 = (blockIdx.x + (long long)i * gridDim.x) * kTcTileM;
+      if (a.B - row0 >= kTcTileM) {
+        TC_TRACE(0x100u | (uint32_t)s);
+        ptx::mbar_arrive_expect_tx(&obs_full[s], tile_bytes);
+        ptx::bulk_g2s(stage, a.obs + row0 * a.in_dim, tile_bytes, &obs_full[s]);
+      } else {
+        ptx::mbar_arrive(&obs_full[s]);      // ragged last tile: the pool reads global memory directly
+      }
+    };
+    if (s < n_local && ptx::elect_one_sync()) load_tile(s);
+    __syncwarp();
+    int phi = 0;
+    for (int i = s; i < n_local; i += 2, phi ^= 1) {
+      uint32_t w_off = 0;
+      for (int l = 0; l < a.n_layers; ++l) {
+        const int kp = tc_layer_kp(a, l), nl = tc_layer_n(a, l);
+        const uint32_t idesc = ptx::make_idesc(fmt, kTcTileM, (uint32_t)nl);
+        // K step of 16 elements = two 8x16B core matrices along K (LBO = 128 B apart); 8-row groups are
+        // kp*16 B apart (SBO); consecutive K steps are 256 B apart (+16 in the descriptor's address field)
+        const uint64_t bdesc0 = ptx::make_smem_desc_nosw(w_base + w_off, 128u, (uint32_t)kp * 16u);
+        const uint32_t src = tmem_base + (uint32_t)s * kTcSlotCols + 128u * (uint32_t)((phi + l) & 1);
+        const uint32_t dst = tmem_base + (uint32_t)s * kTcSlotCols + 128u * (uint32_t)((phi + l + 1) & 1);
+        if (l == 0) {
+          for (int q = 0; q < kTcBlocks; ++q) ptx::mbar_wait(&blk[q], par);
           ptx::tc_fence_after();
-          const int l = lay[s];
-          const int kp = tc_layer_kp(a, l), nl = tc_layer_n(a, l);
-          const uint32_t idesc = ptx::make_idesc(fmt, kTcTileM, (uint32_t)nl);
-          // K step of 16 elements = two 8x16B core matrices along K (LBO = 128 B apart); 8-row groups are
-          // kp*16 B apart (SBO); consecutive K steps are 256 B apart (+16 in the descriptor's address field)
-          const uint64_t bdesc0 = ptx::make_smem_desc_nosw(w_base + woff[s], 128u, (uint32_t)kp * 16u);
-          const int ksteps = kp / 16;
-          const uint32_t d_t = tmem_base + (uint32_t)s * kTcSlotCols;
-          const uint32_t a_t = d_t + 128u;
           if (ptx::elect_one_sync()) {
+            if (i + 2 < n_local) load_tile(i + 2);
             TC_TRACE(0x200u | (uint32_t)(l << 4) | (uint32_t)s);
-            ptx::mma_f16_ts(d_t, a_t, bdesc0, idesc, 0u);
-            for (int j = 1; j < ksteps; ++j)
-              ptx::mma_f16_ts(d_t, a_t + (uint32_t)j * 8u, bdesc0 + (uint64_t)(j * 16), idesc, 1u);
+            const int ksteps = kp / 16;      // A chunk j sits at 32*(j/2) + 8*(j%2), ones inside the data
+            for (int j = 0; j < ksteps; ++j)
+              ptx::mma_f16_ts(dst, src + (uint32_t)(32 * (j >> 1) + 8 * (j & 1)), bdesc0 + (uint64_t)(j * 16), idesc, j > 0 ? 1u : 0u);
             ptx::mma_commit(&acc_full[s]);
             TC_TRACE(0x300u | (uint32_t)(l << 4) | (uint32_t)s);
           }
           __syncwarp();
-          woff[s] += (uint32_t)(kp * nl * 2);
-          if (++lay[s] == a.n_layers) { lay[s] = 0; woff[s] = 0u; --left[s]; }
+        } else {
+#pragma unroll
+          for (int q = 0; q < kTcBlocks; ++q) {
+            const int cb = (q == 1) ? 2 : (q == 2) ? 1 : q;
+            ptx::mbar_wait(&blk[cb], par);
+            ptx::tc_fence_after();
+            if (ptx::elect_one_sync()) {
+              if (q == 0) TC_TRACE(0x200u | (uint32_t)(l << 4) | (uint32_t)s);
+              ptx::mma_f16_ts(dst, src + (uint32_t)(32 * cb), bdesc0 + (uint64_t)(2 * cb * 16), idesc, cb == 0 ? 0u : 1u);
+              ptx::mma_f16_ts(dst, src + (uint32_t)(32 * cb + 8), bdesc0 + (uint64_t)((2 * cb + 1) * 16), idesc, 1u);
+              if (cb == 0) ptx::mma_f16_ts(dst, src + 16u, bdesc0 + (uint64_t)(8 * 16), idesc, 1u);   // bias K step
+              if (q == kTcBlocks - 1) {
+                ptx::mma_commit(&acc_full[s]);
+                TC_TRACE(0x300u | (uint32_t)(l << 4) | (uint32_t)s);
+              }
+            }
+            __syncwarp();
+          }
         }
+        par ^= 1u;
+        w_off += (uint32_t)(kp * nl * 2);
       }
-      s ^= 1;
     }
   } else {
     // ================= worker warps: one pool of 8 warps per slot =================
-    // pool = 4 TMEM lane quarters x 2 column halves; every warp owns 64 columns of each hidden layer (two
-    // 32-column chunks, both loaded up front so the second load and the first store overlap the arithmetic).
+    // pool = 4 TMEM lane quarters x 2 column halves; every warp owns two 32-column blocks of each hidden layer.
     const int s = warp >> 3;                 // slot == pool
     const int quarter = warp & 3;            // TMEM lane quarter this warp may touch (== warp % 4)
-    const int half = (warp >> 2) & 1;        // column half
+    const int half = (warp >> 2) & 1;        // column half: blocks 2*half, 2*half+1
     const uint32_t lane_addr = ((uint32_t)(quarter * 32)) << 16;
-    const uint32_t acc_t = tmem_base + (uint32_t)s * kTcSlotCols + lane_addr;
-    const uint32_t a_t = acc_t + 128u;
+    const uint32_t slot_t = tmem_base + (uint32_t)s * kTcSlotCols + lane_addr;
     const int m = quarter * 32 + lane;       // row inside the tile
     const uint32_t one2 = kFp16 ? 0x3C003C00u : 0x3F803F80u;   // packed (1.0, 1.0)
     const int L = a.n_layers - 1;            // index of the output layer
     const bool out12 = a.out_dim == 12;
     const int n8 = a.k0p / 16;               // layer-0 A operand: chunks of 8 packed columns (16 elements)
     const bool even = (a.in_dim & 1) == 0;
-
-    // constant-one columns of the hidden-layer A operand (K = 128,129), zeros up to K = 143: written once
-    if (half == 0) {
-      const uint32_t ones[8] = {one2, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-      ptx::tmem_st_x8(a_t + (uint32_t)(kTcHidden / 2), ones);
-      ptx::tc_wait_st();
-    }
+    uint64_t* my_blk = &a_blk[s * kTcBlocks + 2 * half];
 
     uint32_t par_acc = 0u;
     int n = 0;
     for (int i = s; i < n_local; i += 2, ++n) {
       const long long row0 = (blockIdx.x + (long long)i * gridDim.x) * kTcTileM;
       const int valid = (int)min((long long)kTcTileM, a.B - row0);
+      const int phi = n & 1;
 
-      // ---- conv: fp32 observation rows -> 16-bit layer-0 A operand in TMEM, constant ones at K = in_dim, in_dim+1
+      // ---- conv: fp32 observation rows -> 16-bit layer-0 A operand, constant ones at K = in_dim, in_dim+1.
+      //      chunk c8 (16 K elements = 8 columns) lands at 32*(c8/2) + 8*(c8%2) of buffer phi
+      const uint32_t a0_t = slot_t + 128u * (uint32_t)phi;
+      TC_TRACE(0xF00u | (uint32_t)s);
       ptx::mbar_wait(&obs_full[s], (uint32_t)(n & 1));
       TC_TRACE(0x400u | (uint32_t)s);
       if (valid == kTcTileM && even) {
         // full tile in shared memory, rows 8-byte aligned: vector loads, uniform per-pair classification
         const float2* r2 = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(stage0 + s * stage_bytes) + (size_t)m * a.in_dim);
+        const int c8_hi = min(n8, 4 * half + 4);
+#pragma unroll 1
+        for (int c8 = 4 * half; c8 < c8_hi; ++c8) {
+          uint32_t q[8];
+          if (c8 * 16 + 16 <= a.in_dim) {
 #pragma unroll
-        for (int it = 0; it < 5; ++it) {
-          const int c8 = half + 2 * it;
-          if (c8 < n8) {
-            uint32_t q[8];
+            for (int j = 0; j < 8; ++j) { const float2 t = r2[c8 * 8 + j]; q[j] = kFp16 ? ptx::pack_f16_sat(t.x, t.y) : ptx::pack_bf16(t.x, t.y); }
+          } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int k = c8 * 16 + 2 * j;
-              if (k < a.in_dim) { const float2 t = r2[k >> 1]; q[j] = kFp16 ? ptx::pack_f16_sat(t.x, t.y) : ptx::pack_bf16(t.x, t.y); }
-              else q[j] = (k == a.in_dim) ? one2 : 0u;
+              float2 t = make_float2(0.f, 0.f);
+              if (k < a.in_dim) t = r2[k >> 1]; else if (k == a.in_dim) t = make_float2(1.f, 1.f);
+              q[j] = kFp16 ? ptx::pack_f16_sat(t.x, t.y) : ptx::pack_bf16(t.x, t.y);
             }
-            ptx::tmem_st_x8(a_t + (uint32_t)c8 * 8u, q);
           }
+          ptx::tmem_st_x8(a0_t + (uint32_t)(32 * (c8 >> 1) + 8 * (c8 & 1)), q);
         }
       } else {
-        // ragged last tile (read straight from global memory) or odd input width: scalar path
         const float* rowp = (valid == kTcTileM) ? reinterpret_cast<const float*>(stage0 + s * stage_bytes) + (size_t)m * a.in_dim
                                                 : a.obs + (row0 + m) * a.in_dim;
-        const bool live = m < valid;
-        for (int c8 = half; c8 < n8; c8 += 2) {
-          uint32_t q[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int k = c8 * 16 + 2 * j;
-            float lo = 0.f, hi = 0.f;
-            if (k < a.in_dim) { if (live) lo = rowp[k]; } else if (k <= a.in_dim + 1) lo = 1.f;
-            if (k + 1 < a.in_dim) { if (live) hi = rowp[k + 1]; } else if (k + 1 <= a.in_dim + 1) hi = 1.f;
-            q[j] = kFp16 ? ptx::pack_f16_sat(lo, hi) : ptx::pack_bf16(lo, hi);
-          }
-          ptx::tmem_st_x8(a_t + (uint32_t)c8 * 8u, q);
-        }
+        tc_conv_slow<kFp16>(a, rowp, m < valid, 4 * half, min(n8, 4 * half + 4), a0_t);
       }
+      TC_TRACE(0xF10u | (uint32_t)s);
       ptx::tc_wait_st();
+      TC_TRACE(0xF20u | (uint32_t)s);
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) { ptx::mbar_arrive(&obs_empty[s]); ptx::mbar_arrive(&a_ready[s]); }
+      TC_TRACE(0xF30u | (uint32_t)s);
+      if (lane == 0) { ptx::mbar_arrive(&my_blk[0]); ptx::mbar_arrive(&my_blk[1]); }
       TC_TRACE(0x500u | (uint32_t)s);
 
-      // ---- hidden layers: accumulator -> ELU -> 16-bit A operand of the next layer (64 columns per warp)
+      // ---- hidden layers: accumulator -> ELU -> 16-bit A operand of the next layer, in place, block by block
       for (int l = 0; l < L; ++l) {
         const bool he = a.has_elu[l] != 0;
         const float c = a.elu_c[l];
-        uint32_t v0[32], v1[32], p0[16], p1[16];
+        const uint32_t d_t = slot_t + 128u * (uint32_t)((phi + 1 + l) & 1) + (uint32_t)(half * 64);
         ptx::mbar_wait(&acc_full[s], par_acc);
         par_acc ^= 1u;
         ptx::tc_fence_after();
-        ptx::tmem_ld_x32(acc_t + (uint32_t)(half * 64), v0);
-        ptx::tmem_ld_x32(acc_t + (uint32_t)(half * 64 + 32), v1);
-        ptx::tc_wait_ld();
         TC_TRACE(0x600u | (uint32_t)(l << 4) | (uint32_t)s);
-        elu_pack32<kFp16>(v0, he, c, p0);
-        ptx::tmem_st_x16(a_t + (uint32_t)(half * 32), p0);
-        elu_pack32<kFp16>(v1, he, c, p1);
-        ptx::tmem_st_x16(a_t + (uint32_t)(half * 32 + 16), p1);
-        TC_TRACE(0xA00u | (uint32_t)(l << 4) | (uint32_t)s);
-        ptx::tc_wait_st();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&a_ready[s]);
-        TC_TRACE(0x700u | (uint32_t)(l << 4) | (uint32_t)s);
+        // rolled loop over 8 groups of 8 columns (small code: it stays in the instruction cache); the load of
+        // group g+1 is in flight while group g is evaluated.  In-place store: the 4 packed words of group g land
+        // on columns that hold accumulator values of groups <= g, all of which are already in registers.
+        uint32_t cur[8], nxt[8], pk[4];
+        ptx::tmem_ld_x8(d_t, cur);
+#pragma unroll 1
+        for (int g = 0; g < 8; g += 2) {
+          ptx::tc_wait_ld();
+          ptx::tmem_ld_x8(d_t + (uint32_t)(8 * g + 8), nxt);
+          elu_pack8<kFp16>(cur, he, c, pk);
+          ptx::tmem_st_x4(d_t + (uint32_t)(32 * (g >> 2) + 4 * (g & 3)), pk);
+          ptx::tc_wait_ld();
+          if (g + 2 < 8) ptx::tmem_ld_x8(d_t + (uint32_t)(8 * g + 16), cur);
+          elu_pack8<kFp16>(nxt, he, c, pk);
+          ptx::tmem_st_x4(d_t + (uint32_t)(32 * (g >> 2) + 4 * (g & 3) + 4), pk);
+          if ((g & 3) == 2) {   // a 32-column block is complete
+            if (half == 0 && g == 2) {   // constant-one columns (K = 128,129; zeros up to 143) in the dead half of block 0
+              const uint32_t ones[8] = {one2, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+              ptx::tmem_st_x8(d_t + 16u, ones);
+            }
+            ptx::tc_wait_st();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&my_blk[g >> 2]);
+            TC_TRACE((g == 2 ? 0xA00u : 0x700u) | (uint32_t)(l << 4) | (uint32_t)s);
+          }
+        }
       }
 
       // ---- output layer (bias already inside the accumulator): (+ELU) (+clamp/mask) (+q_des) -> global
       // 12 outputs: half 0 stores columns 0..7, half 1 columns 8..11; other widths: half 0 does all 16 columns
+      const uint32_t o_t = slot_t + 128u * (uint32_t)((phi + 1 + L) & 1);
       ptx::mbar_wait(&acc_full[s], par_acc);
       par_acc ^= 1u;
       ptx::tc_fence_after();
       TC_TRACE(0x800u | (uint32_t)s);
-      {
-        uint32_t v[16];
-        const int col0 = out12 ? half * 8 : 0;
-        const int nv = out12 ? (half == 0 ? 8 : 4) : 16;
-        const bool active = out12 || half == 0;
-        if (active) {
-          if (nv == 16) ptx::tmem_ld_x16(acc_t, v);
-          else if (nv == 8) ptx::tmem_ld_x8(acc_t, reinterpret_cast<uint32_t(&)[8]>(v));
-          else ptx::tmem_ld_x4(acc_t + 8u, reinterpret_cast<uint32_t(&)[4]>(v));
-        }
+      if (out12 && !a.has_elu[L]) {
+        // the policy's case: 12 outputs, no activation -- half 0 stores columns 0..7, half 1 columns 8..11
+        uint32_t v[8];
+        if (half == 0) ptx::tmem_ld_x8(o_t, v); else ptx::tmem_ld_x4(o_t + 8u, reinterpret_cast<uint32_t(&)[4]>(v));
         ptx::tc_wait_ld();
-        float o[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float x = __uint_as_float(v[j]);
-          if (a.has_elu[L]) x = ((x < 0.f) ? fmaf(ptx::ex2_approx(x), a.elu_c[L], -a.elu_c[L]) : x) * a.out_scale;
-          o[j] = x;
-        }
-        if (active && m < valid) {
+        TC_TRACE(0xF40u | (uint32_t)s);
+        if (m < valid) {
           const long long row = row0 + m;
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v[j]);
           if (a.flags & 1u) {
             const int b0 = a.button0 ? a.button0[row] : 0;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) if (j < nv) o[j] = clamp_mask(o[j], a.action_limit, b0);
+            for (int j = 0; j < 8; ++j) o[j] = clamp_mask(o[j], a.action_limit, b0);
           }
-          float* dst = a.act + row * a.out_dim + col0;
-          if (out12) {
-            reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
-            if (half == 0) reinterpret_cast<float4*>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
-            if ((a.flags & 2u) && a.qdes) {
-              double2* q2 = reinterpret_cast<double2*>(a.qdes + row * kDof + col0);
-#pragma unroll
-              for (int j = 0; j < 8; j += 2)
-                if (j < nv) q2[j >> 1] = make_double2(joint_target(o[j], a.q0[col0 + j], a.action_scale), joint_target(o[j + 1], a.q0[col0 + j + 1], a.action_scale));
+          const int col0 = half * 8;
+          float4* dst = reinterpret_cast<float4*>(a.act + row * 12 + col0);
+          dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+          if (half == 0) dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+          if ((a.flags & 2u) && a.qdes) {
+            double2* q2 = reinterpret_cast<double2*>(a.qdes + row * kDof + col0);
+            q2[0] = make_double2(joint_target(o[0], a.q0[col0 + 0], a.action_scale), joint_target(o[1], a.q0[col0 + 1], a.action_scale));
+            q2[1] = make_double2(joint_target(o[2], a.q0[col0 + 2], a.action_scale), joint_target(o[3], a.q0[col0 + 3], a.action_scale));
+            if (half == 0) {
+              q2[2] = make_double2(joint_target(o[4], a.q0[4], a.action_scale), joint_target(o[5], a.q0[5], a.action_scale));
+              q2[3] = make_double2(joint_target(o[6], a.q0[6], a.action_scale), joint_target(o[7], a.q0[7], a.action_scale));
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) if (j < a.out_dim) dst[j] = o[j];
           }
         }
+      } else if (half == 0) {
+        tc_out_generic(a, o_t, row0 + m, m < valid);
       }
+      TC_TRACE(0xF50u | (uint32_t)s);
       ptx::tc_fence_before();
       TC_TRACE(0x900u | (uint32_t)s);
     }
@@ -374,7 +450,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const TcArgs a) {
   // ---- teardown
   ptx::tc_fence_before();
   block_sync();
-  if (warp == kTcMmaWarp) {
+  if (warp == kTcCtrlWarp0) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<512>(tmem_base);
   }
