@@ -27,6 +27,9 @@ sys.path.insert(0, ROOT)
 
 ALGO_BYTES_PER_INF = 98 * 4 + 12 * 4          # obs in + action out, weights amortised
 ALGO_FLOP_PER_INF = 93696
+# dram__bytes_read.sum + dram__bytes_write.sum of one tc_mlp_kernel launch over 1,048,576 rows, from the ncu
+# --set full capture summarised in profiles/r01_tc_mlp_kernel_final_details.txt (416.0 MB + 63.2 MB)
+NCU_TRAFFIC_BYTES_PER_ROW = (415.977472e6 + 63.183616e6) / 1048576
 METRIC = "policy_inferences_per_sec"
 UNIT = "inferences/s"
 
@@ -85,7 +88,8 @@ def cpu_reference_rate(rows_per_step, steps, warmup, threads=None):
     from go2_onnx_controller_b200 import DEFAULT_MODEL
     coracle.build()
     cm = coracle.CModel(DEFAULT_MODEL)
-    threads = threads or coracle.lib().orc_max_threads()
+    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, so do not ask OpenMP)
+    threads = threads or len(os.sched_getaffinity(0))
     X = oracle.make_obs_d1(rows_per_step, 98, seed=0)
     for _ in range(warmup):
         cm.forward_f32(X[: max(1, rows_per_step // 8)], threads)
@@ -247,7 +251,7 @@ def main():
                 "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3, "api": "go2p_infer_batch_host (pinned host buffers)"},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "tc_mlp_kernel" if args.precision != "fp32" else "sgemm_bias_act_kernel",
+                     "traffic": (NCU_TRAFFIC_BYTES_PER_ROW * rows if args.precision != "fp32" else None), "peak_source": peak_src, "kernel": "tc_mlp_kernel" if args.precision != "fp32" else "sgemm_bias_act_kernel",
                      "algorithmic_bytes_per_inference": ALGO_BYTES_PER_INF,
                      "tensor_frac": ALGO_FLOP_PER_INF * rows / (kernel_ms * 1e-3) / 1e12 / tf_peak},
         "clocks": clocks,
