@@ -202,6 +202,35 @@ __device__ __forceinline__ void b1_layer(const DevLayer& L, const float* __restr
   block_sync();
 }
 
+// Fast GEMV for a 128-wide layer with the weights in shared memory (the resident kernel's case): 512 threads =
+// 128 outputs x 4 K-groups.  Warp w owns outputs 8w..8w+7; lane = g*8 + j, so the 8 lanes of a quarter-warp read
+// 128 contiguous bytes of the k-group-major weights (conflict-free LDS.128) and one broadcast float4 of x; the four
+// partial sums of an output sit in lanes j, j+8, j+16, j+24 and are combined with two shuffles (fixed order).
+__device__ __forceinline__ void b1_layer_n128(const float4* __restrict__ w4, const float* __restrict__ bias, int K4,
+                                              bool has_elu, float alpha, const float4* __restrict__ x4,
+                                              float* __restrict__ y, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 3, o = warp * 8 + (lane & 7);
+  const int per = (K4 + 3) >> 2;
+  const int k0 = g * per, k1 = min(K4, k0 + per);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+  for (int k = k0; k < k1; ++k) {
+    const float4 w = w4[k * 128 + o];
+    const float4 xv = x4[k];
+    a0 = fmaf(w.x, xv.x, a0); a1 = fmaf(w.y, xv.y, a1); a2 = fmaf(w.z, xv.z, a2); a3 = fmaf(w.w, xv.w, a3);
+  }
+  float s = (a0 + a1) + (a2 + a3);
+  s += __shfl_xor_sync(0xffffffffu, s, 8);
+  s += __shfl_xor_sync(0xffffffffu, s, 16);
+  if (g == 0) {
+    s += bias[o];
+    if (has_elu) s = (s < 0.0f) ? alpha * (__expf(s) - 1.0f) : s;   // ex2.approx based: ~1e-6 relative, inside the 1e-5 budget
+    y[o] = s;
+  }
+  block_sync();
+}
+
 // Dynamic shared memory layout (floats): xa[XW] xb[XW] part[kB1Threads] raw[64] state weights...
 __host__ __device__ inline int b1_xw(int max_width) { return ((max_width + 3) & ~3) + 4; }
 
@@ -249,6 +278,20 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_kernel(const B1Args a) {
 
   const int H = a.cc.H;
   const int n_obs = kFrame * H;
+  // which observation element this thread assembles (loop invariant: hoisted out of the message loop).
+  // term offsets H*{0,3,6,9,21,33,45}; widths {3,3,3,12,12,12,4}
+  int t = 0, c = 0, wdt = 3;
+  bool newest = false;
+  if (tid < n_obs) {
+    int off;
+    if (tid < 9 * H) { t = tid / (3 * H); off = t * 3 * H; wdt = 3; }
+    else if (tid < 45 * H) { t = 3 + (tid - 9 * H) / (12 * H); off = 9 * H + (t - 3) * 12 * H; wdt = 12; }
+    else { t = 6; off = 45 * H; wdt = 4; }
+    const int local = tid - off;
+    const int f = local / wdt;
+    c = local - f * wdt;
+    newest = (f == H - 1);
+  }
 
   for (;;) {
     // ---- ingest: every slot is polled by its own thread until its tag shows the next sequence number
@@ -318,21 +361,7 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_kernel(const B1Args a) {
     if (type == MSG_STEP) {
       // ---- A1-A6: term-major history shift + newest frame (controller.cpp:173-212)
       float v = 0.f;
-      int t = 0, c = 0;
-      bool newest = false;
-      if (tid < n_obs) {
-        // term offsets H*{0,3,6,9,21,33,45}; widths {3,3,3,12,12,12,4}
-        const int f49 = tid;
-        int off, wdt;
-        if (f49 < 9 * H) { t = f49 / (3 * H); off = t * 3 * H; wdt = 3; }
-        else if (f49 < 45 * H) { t = 3 + (f49 - 9 * H) / (12 * H); off = 9 * H + (t - 3) * 12 * H; wdt = 12; }
-        else { t = 6; off = 45 * H; wdt = 4; }
-        const int local = f49 - off;
-        const int f = local / wdt;
-        c = local - f * wdt;
-        newest = (f == H - 1);
-        v = newest ? current_term_value(t, c, rw, st, a.cc) : st->obs[tid + wdt];
-      }
+      if (tid < n_obs) v = newest ? current_term_value(t, c, rw, st, a.cc) : st->obs[tid + wdt];
       block_sync();
       if (tid < n_obs) {
         st->obs[tid] = v;
@@ -355,6 +384,12 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_kernel(const B1Args a) {
         wk4 = wrm = wsm + woff;
         bias = wsm + woff + L.Kp * L.N;
         woff += L.Kp * L.N + ((L.N + 3) & ~3);
+      }
+      if (L.N == 128) {   // same code (and bits) whether the weights sit in shared or global memory
+        b1_layer_n128(reinterpret_cast<const float4*>(wk4), bias, L.Kp >> 2, L.has_elu != 0, L.alpha,
+                      reinterpret_cast<const float4*>(x), y, tid);
+        float* tmp = x; x = y; y = tmp;
+        continue;
       }
       b1_layer(L, wk4, wrm, bias, x, y, part, tid);
       float* tmp = x; x = y; y = tmp;
@@ -456,7 +491,9 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_selfdriven_kernel(const B1Ar
     for (int l = 0; l < a.model.n_layers; ++l) {
       const DevLayer& L = a.model.L[l];
       const float* wl = w + woff;
-      b1_layer(L, wl, wl, wl + L.Kp * L.N, x, y, part, tid);
+      if (L.N == 128) b1_layer_n128(reinterpret_cast<const float4*>(wl), wl + L.Kp * L.N, L.Kp >> 2, L.has_elu != 0, L.alpha,
+                                    reinterpret_cast<const float4*>(x), y, tid);
+      else b1_layer(L, wl, wl, wl + L.Kp * L.N, x, y, part, tid);
       woff += L.Kp * L.N + ((L.N + 3) & ~3);
       float* tmp = x; x = y; y = tmp;
     }
