@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE -- ctypes binding of oracle/_build/liboracle.so (the plain-C
-restatement; "parity unpinned", see oracle.h).  Only tests/, smoke() and bench.py's
-cpu_baseline / --impl reference legs may import this."""
+restatement) and of oracle/_ref/libref_controller.so (the reference's own controller.cpp /
+onnx_actor.cpp compiled against the stub headers in oracle/ref_stubs/, see oracle/Makefile).
+Only tests/, smoke() and bench.py's cpu_baseline / --impl reference legs may import this."""
 from __future__ import annotations
 
 import ctypes as C
@@ -11,6 +12,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_build", "liboracle.so")
+REF_LIB_PATH = os.path.join(HERE, "_ref", "libref_controller.so")
 
 ORC_MAX_LAYERS = 16
 ORC_MAX_HIST = 8
@@ -61,9 +63,10 @@ class StepOut(C.Structure):
 
 
 def build(force: bool = False) -> None:
-    """Compile the C restatement."""
+    """Compile the C restatement and, where the reference tree is present, oracle/_ref."""
     if force or not os.path.exists(LIB_PATH):
         subprocess.run(["make", "-C", HERE, LIB_PATH], check=True, capture_output=True)
+    subprocess.run(["make", "-C", HERE, "ref"], check=False, capture_output=True)
 
 
 _lib = None
@@ -174,3 +177,54 @@ class CController:
         a = np.ascontiguousarray(action_raw, np.float32)
         lib().orc_ctrl_post(C.byref(self.s), C.byref(raw), _fp(a), C.byref(out))
         return out
+
+
+class RefController:
+    """The reference's own ONNXController (compiled from /root/reference, oracle/_ref), driven through its node
+    interface.  The model it loads is the reference's onnx_inference/data/model.onnx (GO2_REF_ROOT, default
+    /root/reference; the GPU box has no reference tree, so this class is only usable in the build container)."""
+
+    def __init__(self):
+        if not os.path.exists(REF_LIB_PATH):
+            raise FileNotFoundError(REF_LIB_PATH)
+        L = C.CDLL(REF_LIB_PATH)
+        fp, dp = C.POINTER(C.c_float), C.POINTER(C.c_double)
+        L.refc_create.restype = C.c_void_p
+        L.refc_destroy.argtypes = [C.c_void_p]
+        L.refc_lowstate.argtypes = [C.c_void_p, fp, fp, fp, C.POINTER(C.c_int16)]
+        L.refc_joy.argtypes = [C.c_void_p, fp, C.c_int, C.POINTER(C.c_int32), C.c_int]
+        L.refc_robot.argtypes = [C.c_void_p, dp, dp, C.c_int, C.c_int]
+        L.refc_set_param.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        L.refc_set_param.restype = C.c_int
+        L.refc_step.argtypes = [C.c_void_p, fp, fp, dp, dp, dp]
+        L.refc_step.restype = C.c_int
+        self.L = L
+        self.h = L.refc_create()
+        if not self.h:
+            raise RuntimeError("reference ONNXController could not be constructed")
+
+    def close(self):
+        if self.h:
+            self.L.refc_destroy(self.h)
+            self.h = None
+
+    def feed(self, quat, gyro, foot_force, q, dq, axes, buttons, ready=True, safe=True):
+        """One /lowstate + /joy delivery and the robot's joint state (what publish() reads)."""
+        qf = np.ascontiguousarray(quat, np.float32); gf = np.ascontiguousarray(gyro, np.float32)
+        ff = np.ascontiguousarray(foot_force, np.int16); acc = np.zeros(3, np.float32)
+        self.L.refc_lowstate(self.h, _fp(qf), _fp(gf), _fp(acc), ff.ctypes.data_as(C.POINTER(C.c_int16)))
+        ax = np.ascontiguousarray(axes, np.float32); bt = np.ascontiguousarray(buttons, np.int32)
+        self.L.refc_joy(self.h, _fp(ax), ax.size, bt.ctypes.data_as(C.POINTER(C.c_int32)), bt.size)
+        qd = np.ascontiguousarray(q, np.float64); dqd = np.ascontiguousarray(dq, np.float64)
+        self.L.refc_robot(self.h, _dp(qd), _dp(dqd), int(ready), int(safe))
+
+    def step(self):
+        """Fires the 50 Hz timer.  Returns None if publish() was gated off, else (obs, action, q_des, kp, kd)."""
+        obs = np.zeros(98, np.float32); act = np.zeros(12, np.float32)
+        qd = np.zeros(12, np.float64); kp = np.zeros(12, np.float64); kd = np.zeros(12, np.float64)
+        if not self.L.refc_step(self.h, _fp(obs), _fp(act), _dp(qd), _dp(kp), _dp(kd)):
+            return None
+        return obs, act, qd, kp, kd
+
+    def set_param(self, name: str, value: float) -> bool:
+        return bool(self.L.refc_set_param(self.h, name.encode(), float(value)))

@@ -2,12 +2,16 @@
  * path.  Linked / loaded only by tests/, __graft_entry__.smoke() and the
  * cpu_baseline / --impl reference legs of bench.py.  Never by the product.
  *
- * PARITY STATUS: "parity unpinned" -- the ONNX Runtime 1.20.1 binary that holds
- * A7's arithmetic is absent, the reference holds no golden vector, and
- * controller.cpp cannot be compiled here (ROS 2 / Eigen absent), so no
- * oracle/_ref exists.  Pinned instead by three independent restatements
- * (numpy fp64, this C code, torch-CPU fp64) that agree to 2e-15 and by the
- * known-answer vectors of SURVEY.md Appendix D (tests/test_oracle.py).
+ * PARITY STATUS
+ *   A7 (policy forward): "parity unpinned" -- the ONNX Runtime 1.20.1 binary that holds
+ *   its arithmetic is absent and the reference holds no golden vector; pinned instead by
+ *   three independent restatements (numpy fp64, this C code, torch-CPU fp64) that agree
+ *   to 2e-15 and by the known-answer vectors of SURVEY.md Appendix D.
+ *   A1-A6, A9, A11 and the ONNXActor wrapper: pinned to the reference's OWN
+ *   controller.cpp / onnx_actor.cpp, compiled from /root/reference against stub ROS /
+ *   Eigen / ORT headers (oracle/Makefile -> oracle/_ref); bit-identical over the 400-step
+ *   closed-loop fixture (tests/test_ref_controller.py, tests/golden/ref_controller_trace.npz).
+ *   Caveat: the stub's Quaternion arithmetic is itself a restatement of Eigen 3.4.
  */
 #ifndef GO2_ORACLE_H
 #define GO2_ORACLE_H

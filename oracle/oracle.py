@@ -12,12 +12,11 @@ PARITY STATUS
     restatement follows the ONNX opset-17 operator definitions of the graph
     stored in onnx_inference/data/model.onnx and is cross-checked against an
     independent torch-CPU fp64 evaluation (tests/golden/make_golden.py).
-  * A1-A6, A9-A11 (observation assembly / action post-processing) -- restated from
-    controller.cpp / controller.hpp with the promotion rules of SURVEY.md App. C; the
-    reference's controller.cpp cannot be compiled here (ROS 2, Eigen,
-    go2_control_interface absent), so these rows are cross-checked between this numpy
-    restatement and the plain-C one (oracle_ctrl.c), bit for bit, not against a
-    reference binary.
+  * A1-A6, A9-A11 (observation assembly / action post-processing) -- pinned against the
+    reference's own controller.cpp compiled from where it lies (oracle/Makefile ->
+    oracle/_ref/libref_controller.so; external ROS / Eigen / ORT headers replaced by the
+    stubs under oracle/ref_stubs/): bit-identical over the closed-loop fixture
+    (tests/test_ref_controller.py).  The stub's quaternion arithmetic restates Eigen 3.4.
 
 Every function cites the reference file:line it restates.
 """

@@ -111,6 +111,24 @@ def main():
                         **{f"raw_{k}": v for k, v in raw_arr.items()}, **{k: np.stack(v) for k, v in rec.items()})
     print("closed loop:", n, "steps; buttons pressed:", int(raw_arr["button0"].sum()))
 
+    # the same raw-state stream through the reference's OWN controller.cpp / onnx_actor.cpp (oracle/_ref, compiled
+    # from /root/reference against stub headers; A7 inside it is the C fp32 restatement) -> committed fixture, so the
+    # restated pre/post-processing stays pinned to the reference's code where /root/reference does not exist
+    if os.path.exists(coracle.REF_LIB_PATH) and os.path.exists(REF):
+        rc = coracle.RefController()
+        tr = {k: [] for k in ("obs", "action", "q_des", "kp", "kd")}
+        for r in raws:
+            axes = r.axes if r.joy_valid else np.zeros(0, np.float32)
+            rc.feed(r.quat, r.gyro, r.foot_force, r.q.astype(np.float64), r.dq.astype(np.float64), axes, [int(r.button0)])
+            out = rc.step()
+            for k, v in zip(tr, out):
+                tr[k].append(v.copy())
+        rc.close()
+        np.savez_compressed(os.path.join(HERE, "ref_controller_trace.npz"), **{k: np.stack(v) for k, v in tr.items()})
+        print("reference-controller trace written:", len(raws), "steps")
+    else:
+        print("oracle/_ref not available: ref_controller_trace.npz left untouched")
+
 
 if __name__ == "__main__":
     main()

@@ -107,6 +107,8 @@ def test_fused_step_closed_loop_vs_oracle(torch_cuda, model_path, policy, golden
     (so every step is an exact comparison) and the free-running golden trajectory bounds the drift."""
     g = golden_loop
     n = g["obs"].shape[0]
+    # trace recorded from the reference's own compiled controller.cpp (tests/golden/make_golden.py, oracle/_ref)
+    ref_tr = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "ref_controller_trace.npz"))
     ctl = Go2Controller(model_path)
     st = oracle.ControllerState(H=2)
     try:
@@ -123,6 +125,12 @@ def test_fused_step_closed_loop_vs_oracle(torch_cuda, model_path, policy, golden
             ulp_g = max(ulp_g, int(ulp))
             assert ulp <= 1, (i, d_obs[:6], so.obs[:6])
             assert np.array_equal(bits(d_obs[6:]), bits(so.obs[6:])), i
+            # everything in the observation that does not pass through the policy (all but the previous-action
+            # block 66..89) must equal what the reference's compiled publish() produced, bit for bit
+            ro = ref_tr["obs"][i]
+            assert np.array_equal(bits(d_obs[6:66]), bits(ro[6:66])) and np.array_equal(bits(d_obs[90:]), bits(ro[90:])), i
+            assert np.abs(bits(d_obs[:6]).astype(np.int64) - bits(ro[:6]).astype(np.int64)).max() <= 1, i
+            assert np.abs(d_obs[66:90] - ro[66:90]).max() <= 1e-4, i
             assert np.array_equal(bits(d_act), bits(so.action)), i                    # A9 bit-exact
             assert np.array_equal(d_qdes, so.q_des), i                                # A11 bit-exact (double)
             assert out.kp == so.kp and out.kd == so.kd, i
