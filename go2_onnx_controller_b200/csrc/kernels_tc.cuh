@@ -31,14 +31,17 @@
 #include "policy_dev.cuh"
 #include "ptx_sm100.cuh"
 
+#ifndef GO2P_TC_POLY_PAIRS
+#define GO2P_TC_POLY_PAIRS 2
+#endif
+
 namespace go2p {
 
 constexpr int kTcTileM = 128;
 constexpr int kTcHidden = 128;     // every hidden width handled by this kernel
 constexpr int kTcOutPad = 16;      // last layer N padded to 16 (smallest UMMA N at M=128)
 constexpr int kTcBiasK = 16;       // extra K block carrying the two constant-one columns (bias hi / lo)
-constexpr int kTcWorkers = 16;     // warps 0..7 serve slot 0, 8..15 slot 1: 4 TMEM lane quarters (warp % 4) x 2 column halves
-constexpr int kTcPool = 8;         // worker warps per slot
+constexpr int kTcWorkers = 16;     // warps 0..15: one pool, 4 TMEM lane quarters (warp % 4) x 4 column blocks (warp / 4)
 constexpr int kTcCtrlWarp0 = 16;      // warps 16,17: per-slot control warp = bulk-copy producer + MMA issuer; warp 16 owns TMEM
 constexpr int kTcThreads = (kTcWorkers + 2) * 32;
 constexpr int kTcSlotCols = 256;   // TMEM columns per slot: two 128-column ping-pong buffers
@@ -103,6 +106,28 @@ __device__ __forceinline__ void elu_pack8(const uint32_t (&v)[8], bool has_elu, 
     if (has_elu) {
       const float f0 = fmaf(ptx::ex2_approx(z0), c, nc);
       const float f1 = fmaf(ptx::ex2_approx(z1), c, nc);
+      const uint32_t fp = kFp16 ? ptx::pack_f16_sat(f0, f1) : ptx::pack_bf16(f0, f1);
+      p[j] = kFp16 ? ptx::select_neg_f16x2(zp, fp) : ptx::select_neg_bf16x2(zp, fp);
+    } else {
+      p[j] = zp;
+    }
+  }
+}
+
+// same on 16 accumulator columns -> 8 packed words
+constexpr int kTcPolyPairs = GO2P_TC_POLY_PAIRS;   // of every 8 column pairs, this many take the FMA-pipe exponential
+
+template <bool kFp16>
+__device__ __forceinline__ void elu_pack16(const uint32_t (&v)[16], bool has_elu, float c, uint32_t (&p)[8]) {
+  const float nc = -c;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float z0 = __uint_as_float(v[2 * j]), z1 = __uint_as_float(v[2 * j + 1]);
+    const uint32_t zp = kFp16 ? ptx::pack_f16_sat(z0, z1) : ptx::pack_bf16(z0, z1);
+    if (has_elu) {
+      const bool poly = kFp16 && j >= 8 - kTcPolyPairs;   // bf16 keeps the MUFU everywhere (its budget has no slack)
+      const float f0 = fmaf(poly ? ptx::ex2_poly(z0) : ptx::ex2_approx(z0), c, nc);
+      const float f1 = fmaf(poly ? ptx::ex2_poly(z1) : ptx::ex2_approx(z1), c, nc);
       const uint32_t fp = kFp16 ? ptx::pack_f16_sat(f0, f1) : ptx::pack_bf16(f0, f1);
       p[j] = kFp16 ? ptx::select_neg_f16x2(zp, fp) : ptx::select_neg_bf16x2(zp, fp);
     } else {
@@ -229,7 +254,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const TcArgs a) {
   if (warp >= kTcCtrlWarp0) {
     // ================= control warp of slot s: bulk-copy producer + MMA issuer =================
     // One warp per slot walks that slot's tiles and layers and blocks on the A-ready barrier of each 32-column
-    // block in the fixed order 0,2,1,3 (the order the pool finishes them), issuing that block's K steps at once:
+    // block in the fixed order 0,1,2,3, issuing that block's K steps at once:
     // the MMA trails the epilogue, and the fixed order keeps the fp32 accumulation order (every output bit)
     // independent of timing.  Layer 0 waits for all four blocks (its first K step overwrites the buffer the
     // previous tile's output epilogue reads, and a warp signals its blocks only after that read); at that point
@@ -279,7 +304,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const TcArgs a) {
         } else {
 #pragma unroll
           for (int q = 0; q < kTcBlocks; ++q) {
-            const int cb = (q == 1) ? 2 : (q == 2) ? 1 : q;
+            const int cb = q;
             ptx::mbar_wait(&blk[cb], par);
             ptx::tc_fence_after();
             if (ptx::elect_one_sync()) {
@@ -300,150 +325,141 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const TcArgs a) {
       }
     }
   } else {
-    // ================= worker warps: one pool of 8 warps per slot =================
-    // pool = 4 TMEM lane quarters x 2 column halves; every warp owns two 32-column blocks of each hidden layer.
-    const int s = warp >> 3;                 // slot == pool
+    // ================= worker warps: one pool of 16 warps walks the job list of both slots =================
+    // pool = 4 TMEM lane quarters x 4 column blocks (warp = cb*4 + quarter): every warp owns one 32-column block.
+    // Job order per pair of tiles: conv(s0) conv(s1) | E(l,s0) E(l,s1) for every hidden layer | out(s0) out(s1).
+    // While the pool works on one slot, the other slot's next-layer MMA (which trailed its epilogue block by block)
+    // completes, so the pool never waits for a hand-off in steady state and the MUFU pipe has 4 warps per scheduler.
     const int quarter = warp & 3;            // TMEM lane quarter this warp may touch (== warp % 4)
-    const int half = (warp >> 2) & 1;        // column half: blocks 2*half, 2*half+1
+    const int cb = warp >> 2;                // 32-column block
     const uint32_t lane_addr = ((uint32_t)(quarter * 32)) << 16;
-    const uint32_t slot_t = tmem_base + (uint32_t)s * kTcSlotCols + lane_addr;
     const int m = quarter * 32 + lane;       // row inside the tile
     const uint32_t one2 = kFp16 ? 0x3C003C00u : 0x3F803F80u;   // packed (1.0, 1.0)
     const int L = a.n_layers - 1;            // index of the output layer
     const bool out12 = a.out_dim == 12;
     const int n8 = a.k0p / 16;               // layer-0 A operand: chunks of 8 packed columns (16 elements)
     const bool even = (a.in_dim & 1) == 0;
-    uint64_t* my_blk = &a_blk[s * kTcBlocks + 2 * half];
 
-    uint32_t par_acc = 0u;
-    int n = 0;
-    for (int i = s; i < n_local; i += 2, ++n) {
-      const long long row0 = (blockIdx.x + (long long)i * gridDim.x) * kTcTileM;
-      const int valid = (int)min((long long)kTcTileM, a.B - row0);
-      const int phi = n & 1;
+    uint32_t par_acc[2] = {0u, 0u};
+    for (int pair = 0; pair * 2 < n_local; ++pair) {
+      const int ns = min(2, n_local - pair * 2);
+      const int phi = pair & 1;
 
-      // ---- conv: fp32 observation rows -> 16-bit layer-0 A operand, constant ones at K = in_dim, in_dim+1.
-      //      chunk c8 (16 K elements = 8 columns) lands at 32*(c8/2) + 8*(c8%2) of buffer phi
-      const uint32_t a0_t = slot_t + 128u * (uint32_t)phi;
-      TC_TRACE(0xF00u | (uint32_t)s);
-      ptx::mbar_wait(&obs_full[s], (uint32_t)(n & 1));
-      TC_TRACE(0x400u | (uint32_t)s);
-      if (valid == kTcTileM && even) {
-        // full tile in shared memory, rows 8-byte aligned: vector loads, uniform per-pair classification
-        const float2* r2 = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(stage0 + s * stage_bytes) + (size_t)m * a.in_dim);
-        const int c8_hi = min(n8, 4 * half + 4);
+      // ---- conv(s): fp32 observation rows -> 16-bit layer-0 A operand, constant ones at K = in_dim, in_dim+1.
+      //      chunk c8 (16 K elements = 8 columns) lands at 32*(c8/2) + 8*(c8%2) of buffer phi: block cb = chunks 2cb, 2cb+1
+      for (int s = 0; s < ns; ++s) {
+        const long long row0 = (blockIdx.x + (long long)(pair * 2 + s) * gridDim.x) * kTcTileM;
+        const int valid = (int)min((long long)kTcTileM, a.B - row0);
+        const uint32_t a0_t = tmem_base + (uint32_t)s * kTcSlotCols + lane_addr + 128u * (uint32_t)phi;
+        ptx::mbar_wait(&obs_full[s], (uint32_t)(pair & 1));
+        TC_TRACE(0x400u | (uint32_t)s);
+        const int c8_hi = min(n8, 2 * cb + 2);
+        if (valid == kTcTileM && even) {
+          // full tile in shared memory, rows 8-byte aligned: vector loads, uniform per-pair classification
+          const float2* r2 = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(stage0 + s * stage_bytes) + (size_t)m * a.in_dim);
 #pragma unroll 1
-        for (int c8 = 4 * half; c8 < c8_hi; ++c8) {
-          uint32_t q[8];
-          if (c8 * 16 + 16 <= a.in_dim) {
+          for (int c8 = 2 * cb; c8 < c8_hi; ++c8) {
+            uint32_t q[8];
+            if (c8 * 16 + 16 <= a.in_dim) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { const float2 t = r2[c8 * 8 + j]; q[j] = kFp16 ? ptx::pack_f16_sat(t.x, t.y) : ptx::pack_bf16(t.x, t.y); }
-          } else {
+              for (int j = 0; j < 8; ++j) { const float2 t = r2[c8 * 8 + j]; q[j] = kFp16 ? ptx::pack_f16_sat(t.x, t.y) : ptx::pack_bf16(t.x, t.y); }
+            } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int k = c8 * 16 + 2 * j;
-              float2 t = make_float2(0.f, 0.f);
-              if (k < a.in_dim) t = r2[k >> 1]; else if (k == a.in_dim) t = make_float2(1.f, 1.f);
-              q[j] = kFp16 ? ptx::pack_f16_sat(t.x, t.y) : ptx::pack_bf16(t.x, t.y);
+              for (int j = 0; j < 8; ++j) {
+                const int k = c8 * 16 + 2 * j;
+                float2 t = make_float2(0.f, 0.f);
+                if (k < a.in_dim) t = r2[k >> 1]; else if (k == a.in_dim) t = make_float2(1.f, 1.f);
+                q[j] = kFp16 ? ptx::pack_f16_sat(t.x, t.y) : ptx::pack_bf16(t.x, t.y);
+              }
             }
+            ptx::tmem_st_x8(a0_t + (uint32_t)(32 * (c8 >> 1) + 8 * (c8 & 1)), q);
           }
-          ptx::tmem_st_x8(a0_t + (uint32_t)(32 * (c8 >> 1) + 8 * (c8 & 1)), q);
+        } else {
+          const float* rowp = (valid == kTcTileM) ? reinterpret_cast<const float*>(stage0 + s * stage_bytes) + (size_t)m * a.in_dim
+                                                  : a.obs + (row0 + m) * a.in_dim;
+          tc_conv_slow<kFp16>(a, rowp, m < valid, 2 * cb, c8_hi, a0_t);
         }
-      } else {
-        const float* rowp = (valid == kTcTileM) ? reinterpret_cast<const float*>(stage0 + s * stage_bytes) + (size_t)m * a.in_dim
-                                                : a.obs + (row0 + m) * a.in_dim;
-        tc_conv_slow<kFp16>(a, rowp, m < valid, 4 * half, min(n8, 4 * half + 4), a0_t);
+        ptx::tc_wait_st();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&a_blk[s * kTcBlocks + cb]);
+        TC_TRACE(0x500u | (uint32_t)s);
       }
-      TC_TRACE(0xF10u | (uint32_t)s);
-      ptx::tc_wait_st();
-      TC_TRACE(0xF20u | (uint32_t)s);
-      ptx::tc_fence_before();
-      __syncwarp();
-      TC_TRACE(0xF30u | (uint32_t)s);
-      if (lane == 0) { ptx::mbar_arrive(&my_blk[0]); ptx::mbar_arrive(&my_blk[1]); }
-      TC_TRACE(0x500u | (uint32_t)s);
 
-      // ---- hidden layers: accumulator -> ELU -> 16-bit A operand of the next layer, in place, block by block
+      // ---- E(l,s): accumulator block -> ELU -> 16-bit A operand of the next layer, in place
       for (int l = 0; l < L; ++l) {
         const bool he = a.has_elu[l] != 0;
         const float c = a.elu_c[l];
-        const uint32_t d_t = slot_t + 128u * (uint32_t)((phi + 1 + l) & 1) + (uint32_t)(half * 64);
-        ptx::mbar_wait(&acc_full[s], par_acc);
-        par_acc ^= 1u;
-        ptx::tc_fence_after();
-        TC_TRACE(0x600u | (uint32_t)(l << 4) | (uint32_t)s);
-        // rolled loop over 8 groups of 8 columns (small code: it stays in the instruction cache); the load of
-        // group g+1 is in flight while group g is evaluated.  In-place store: the 4 packed words of group g land
-        // on columns that hold accumulator values of groups <= g, all of which are already in registers.
-        uint32_t cur[8], nxt[8], pk[4];
-        ptx::tmem_ld_x8(d_t, cur);
-#pragma unroll 1
-        for (int g = 0; g < 8; g += 2) {
+        for (int s = 0; s < ns; ++s) {
+          const uint32_t d_t = tmem_base + (uint32_t)s * kTcSlotCols + lane_addr + 128u * (uint32_t)((phi + 1 + l) & 1) + (uint32_t)(cb * 32);
+          ptx::mbar_wait(&acc_full[s], par_acc[s]);
+          par_acc[s] ^= 1u;
+          ptx::tc_fence_after();
+          TC_TRACE(0x600u | (uint32_t)(l << 4) | (uint32_t)s);
+          // rolled loop over 4 groups of 8 columns (small code: it stays in the instruction cache); the load of group
+          // g+1 is in flight while group g is evaluated.  In-place store: the 4 packed words of group g land on
+          // columns that hold accumulator values of groups <= g, all of which are already in registers.
+          // two halves of 16 columns: the second half's load is in flight while the first is evaluated.  In-place
+          // store: the 8 packed words of half h land on columns 8h..8h+7, which hold accumulator values of half 0 only.
+          uint32_t cur[16], nxt[16], pk[8];
+          ptx::tmem_ld_x16(d_t, cur);
+          ptx::tmem_ld_x16(d_t + 16u, nxt);
           ptx::tc_wait_ld();
-          ptx::tmem_ld_x8(d_t + (uint32_t)(8 * g + 8), nxt);
-          elu_pack8<kFp16>(cur, he, c, pk);
-          ptx::tmem_st_x4(d_t + (uint32_t)(32 * (g >> 2) + 4 * (g & 3)), pk);
-          ptx::tc_wait_ld();
-          if (g + 2 < 8) ptx::tmem_ld_x8(d_t + (uint32_t)(8 * g + 16), cur);
-          elu_pack8<kFp16>(nxt, he, c, pk);
-          ptx::tmem_st_x4(d_t + (uint32_t)(32 * (g >> 2) + 4 * (g & 3) + 4), pk);
-          if ((g & 3) == 2) {   // a 32-column block is complete
-            if (half == 0 && g == 2) {   // constant-one columns (K = 128,129; zeros up to 143) in the dead half of block 0
-              const uint32_t ones[8] = {one2, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-              ptx::tmem_st_x8(d_t + 16u, ones);
-            }
-            ptx::tc_wait_st();
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&my_blk[g >> 2]);
-            TC_TRACE((g == 2 ? 0xA00u : 0x700u) | (uint32_t)(l << 4) | (uint32_t)s);
+          elu_pack16<kFp16>(cur, he, c, pk);
+          ptx::tmem_st_x8(d_t, pk);
+          elu_pack16<kFp16>(nxt, he, c, pk);
+          ptx::tmem_st_x8(d_t + 8u, pk);
+          if (cb == 0) {   // constant-one columns (K = 128,129; zeros up to 143) in the dead half of block 0
+            const uint32_t ones[8] = {one2, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            ptx::tmem_st_x8(d_t + 16u, ones);
           }
+          ptx::tc_wait_st();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&a_blk[s * kTcBlocks + cb]);
+          TC_TRACE(0x700u | (uint32_t)(l << 4) | (uint32_t)s);
         }
       }
 
-      // ---- output layer (bias already inside the accumulator): (+ELU) (+clamp/mask) (+q_des) -> global
-      // 12 outputs: half 0 stores columns 0..7, half 1 columns 8..11; other widths: half 0 does all 16 columns
-      const uint32_t o_t = slot_t + 128u * (uint32_t)((phi + 1 + L) & 1);
-      ptx::mbar_wait(&acc_full[s], par_acc);
-      par_acc ^= 1u;
-      ptx::tc_fence_after();
-      TC_TRACE(0x800u | (uint32_t)s);
-      if (out12 && !a.has_elu[L]) {
-        // the policy's case: 12 outputs, no activation -- half 0 stores columns 0..7, half 1 columns 8..11
-        uint32_t v[8];
-        if (half == 0) ptx::tmem_ld_x8(o_t, v); else ptx::tmem_ld_x4(o_t + 8u, reinterpret_cast<uint32_t(&)[4]>(v));
-        ptx::tc_wait_ld();
-        TC_TRACE(0xF40u | (uint32_t)s);
-        if (m < valid) {
-          const long long row = row0 + m;
-          float o[8];
+      // ---- out(s) (bias already inside the accumulator): (+ELU) (+clamp/mask) (+q_des) -> global
+      for (int s = 0; s < ns; ++s) {
+        const long long row0 = (blockIdx.x + (long long)(pair * 2 + s) * gridDim.x) * kTcTileM;
+        const int valid = (int)min((long long)kTcTileM, a.B - row0);
+        const uint32_t o_t = tmem_base + (uint32_t)s * kTcSlotCols + lane_addr + 128u * (uint32_t)((phi + 1 + L) & 1);
+        ptx::mbar_wait(&acc_full[s], par_acc[s]);
+        par_acc[s] ^= 1u;
+        ptx::tc_fence_after();
+        TC_TRACE(0x800u | (uint32_t)s);
+        if (out12 && !a.has_elu[L]) {
+          // the policy's case: 12 outputs, no activation -- column block cb < 3 stores one float4 of every row
+          if (cb < 3) {
+            uint32_t v[4];
+            ptx::tmem_ld_x4(o_t + (uint32_t)(cb * 4), v);
+            ptx::tc_wait_ld();
+            if (m < valid) {
+              const long long row = row0 + m;
+              float o[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v[j]);
-          if (a.flags & 1u) {
-            const int b0 = a.button0 ? a.button0[row] : 0;
+              for (int j = 0; j < 4; ++j) o[j] = __uint_as_float(v[j]);
+              if (a.flags & 1u) {
+                const int b0 = a.button0 ? a.button0[row] : 0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = clamp_mask(o[j], a.action_limit, b0);
-          }
-          const int col0 = half * 8;
-          float4* dst = reinterpret_cast<float4*>(a.act + row * 12 + col0);
-          dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-          if (half == 0) dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-          if ((a.flags & 2u) && a.qdes) {
-            double2* q2 = reinterpret_cast<double2*>(a.qdes + row * kDof + col0);
-            q2[0] = make_double2(joint_target(o[0], a.q0[col0 + 0], a.action_scale), joint_target(o[1], a.q0[col0 + 1], a.action_scale));
-            q2[1] = make_double2(joint_target(o[2], a.q0[col0 + 2], a.action_scale), joint_target(o[3], a.q0[col0 + 3], a.action_scale));
-            if (half == 0) {
-              q2[2] = make_double2(joint_target(o[4], a.q0[4], a.action_scale), joint_target(o[5], a.q0[5], a.action_scale));
-              q2[3] = make_double2(joint_target(o[6], a.q0[6], a.action_scale), joint_target(o[7], a.q0[7], a.action_scale));
+                for (int j = 0; j < 4; ++j) o[j] = clamp_mask(o[j], a.action_limit, b0);
+              }
+              reinterpret_cast<float4*>(a.act + row * 12)[cb] = make_float4(o[0], o[1], o[2], o[3]);
+              if ((a.flags & 2u) && a.qdes) {
+                double2* q2 = reinterpret_cast<double2*>(a.qdes + row * kDof + cb * 4);
+                q2[0] = make_double2(joint_target(o[0], a.q0[cb * 4 + 0], a.action_scale), joint_target(o[1], a.q0[cb * 4 + 1], a.action_scale));
+                q2[1] = make_double2(joint_target(o[2], a.q0[cb * 4 + 2], a.action_scale), joint_target(o[3], a.q0[cb * 4 + 3], a.action_scale));
+              }
             }
           }
+        } else if (cb == 0) {
+          tc_out_generic(a, o_t, row0 + m, m < valid);
         }
-      } else if (half == 0) {
-        tc_out_generic(a, o_t, row0 + m, m < valid);
+        ptx::tc_fence_before();
+        TC_TRACE(0x900u | (uint32_t)s);
       }
-      TC_TRACE(0xF50u | (uint32_t)s);
-      ptx::tc_fence_before();
-      TC_TRACE(0x900u | (uint32_t)s);
     }
   }
 

@@ -199,6 +199,20 @@ __device__ __forceinline__ uint32_t select_neg_bf16x2(uint32_t z, uint32_t neg) 
   asm("set.lt.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(z), "r"(0u));
   return (neg & m) | (z & ~m);
 }
+// 2^x for x <= 0 on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + r via the 1.5*2^23 trick,
+// degree-3 minimax polynomial for 2^r on [-0.5, 0.5] (max relative error 7.5e-5, below half an fp16 ulp), exponent
+// patched in with an integer add.  Inputs below -24 are clamped (2^-24 is far below the resolution of c*(2^x - 1));
+// results for x > 0 are garbage by design: the ELU select discards them.  Used for a fraction of the columns so the
+// MUFU pipe (16 lanes/clk/SM, the per-SM floor of this policy) is not the only exponential unit.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -24.0f);
+  const float t = __fadd_rn(x, 12582912.0f);
+  const float r = __fsub_rn(x, __fsub_rn(t, 12582912.0f));
+  float p = fmaf(0.055171653628349304f, r, 0.2426111251115799f);
+  p = fmaf(p, r, 0.6932609677314758f);
+  p = fmaf(p, r, 0.9999280571937561f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+}
 __device__ __forceinline__ float ex2_approx(float x) {
 #ifdef GO2P_EXP_NOMUFU
   return x + 1.0f;   // timing experiment only: wrong numerics, no MUFU
