@@ -104,6 +104,10 @@ __device__ __forceinline__ float vel_cmd_component(const float* axes, int c) {
   return __fmul_rn(a3, a1);
 }
 
+// one observation frame: term widths {3,3,3,12,12,12,4} at offsets {0,3,6,9,21,33,45}
+__device__ __forceinline__ int frame_width(int t) { return t < 3 ? 3 : (t < 6 ? 12 : 4); }
+__device__ __forceinline__ int frame_offset(int t) { return t < 3 ? 3 * t : (t < 6 ? 9 + 12 * (t - 3) : 45); }
+
 // The newest-frame value of observation term t, component c (A1-A4).
 __device__ __forceinline__ float current_term_value(int t, int c, const uint32_t* rw, const B1State* st,
                                                     const CtrlConst& cc) {
@@ -360,8 +364,15 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_kernel(const B1Args a) {
 
     if (type == MSG_STEP) {
       // ---- A1-A6: term-major history shift + newest frame (controller.cpp:173-212)
+      // the 49 newest-frame values are produced one term per warp (warp t, lane c): no intra-warp divergence between
+      // the gravity projection, the double-precision vel_cmd / q - q0 paths and the plain copies
+      {
+        const int ft = tid >> 5, fc = tid & 31;
+        if (ft < 7 && fc < frame_width(ft)) part[frame_offset(ft) + fc] = current_term_value(ft, fc, rw, st, a.cc);
+      }
+      block_sync();
       float v = 0.f;
-      if (tid < n_obs) v = newest ? current_term_value(t, c, rw, st, a.cc) : st->obs[tid + wdt];
+      if (tid < n_obs) v = newest ? part[frame_offset(t) + c] : st->obs[tid + wdt];
       block_sync();
       if (tid < n_obs) {
         st->obs[tid] = v;
@@ -473,16 +484,21 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_selfdriven_kernel(const B1Ar
   for (int s = 0; s < steps; ++s) {
     if (tid < kRawWords) rw[tid] = raws[(size_t)(s % n_raws) * kRawWords + tid];
     block_sync();
-    float v = 0.f; int t = 0, c = 0; bool newest = false;
+    float v = 0.f; int t = 0, c = 0, wdt = 3; bool newest = false;
     if (tid < n_obs) {
-      int off, wdt;
+      int off;
       if (tid < 9 * H) { t = tid / (3 * H); off = t * 3 * H; wdt = 3; }
       else if (tid < 45 * H) { t = 3 + (tid - 9 * H) / (12 * H); off = 9 * H + (t - 3) * 12 * H; wdt = 12; }
       else { t = 6; off = 45 * H; wdt = 4; }
       const int local = tid - off; const int f = local / wdt; c = local - f * wdt;
       newest = (f == H - 1);
-      v = newest ? current_term_value(t, c, rw, st, a.cc) : st->obs[tid + wdt];
     }
+    {
+      const int ft = tid >> 5, fc = tid & 31;
+      if (ft < 7 && fc < frame_width(ft)) part[frame_offset(ft) + fc] = current_term_value(ft, fc, rw, st, a.cc);
+    }
+    block_sync();
+    if (tid < n_obs) v = newest ? part[frame_offset(t) + c] : st->obs[tid + wdt];
     block_sync();
     if (tid < n_obs) { st->obs[tid] = v; xa[tid] = v; if (newest && t == 2) st->vel_cmd[c] = v; }
     if (tid >= a.model.in_dim && tid < a.model.L[0].Kp) xa[tid] = 0.f;
