@@ -220,6 +220,21 @@ def main():
         ref = oracle.clamp_mask(oracle.forward(pol, d_obs[idx].cpu().numpy()).astype(np.float32), 0)
         got = d_act[idx].cpu().numpy()
         parity_err = float(np.abs(got - ref).max())
+    # ---- BASELINE.json configs[2]: batch 4096 on one GPU -- single-launch latency and pipelined throughput
+    small = None
+    if rank == 0:
+        sb = 4096
+        lat = []
+        for _ in range(200):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            pb.infer_device(d_obs.data_ptr(), d_act.data_ptr(), sb, prec, stream, d_b0.data_ptr(), None, flags)
+            a1.record()
+            a1.synchronize()
+            lat.append(a0.elapsed_time(a1) * 1e3)
+        ms_pipe = pb.time_device(d_obs.data_ptr(), d_act.data_ptr(), sb, prec, 200, stream, d_b0.data_ptr(), None, flags)
+        small = {"batch": sb, "single_launch_us_p50": float(np.percentile(lat, 50)), "single_launch_us_p99": float(np.percentile(lat, 99)),
+                 "pipelined_inferences_per_sec": sb * 200 / (ms_pipe * 1e-3), "note": "L2-resident (1.8 MB), launch-latency bound"}
     # ---- e2e: HOST buffers through the C ABI, copies inside the timed region
     e2e_steps = args.e2e_steps or min(args.steps, 10)
     hx = pb.pinned((rows, 98))
@@ -258,6 +273,7 @@ def main():
     }
     if rank == 0:
         line["parity_max_abs_err_vs_oracle"] = parity_err
+        line["batch4096"] = small
     if rank == 0 and world == 1 and not args.no_b1:
         # BASELINE.json configs[1]: batch-1 closed loop, fused pre/post, resident kernel
         from oracle import oracle as _o

@@ -70,8 +70,12 @@ __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   }
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  // fast path inline (a handful of instructions); the watchdog loop lives out of line to keep hot code small
-  if (!mbar_try_wait(bar, parity) && !mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
+  // fast path inline: a short rolled retry loop (every failed try_wait already sleeps in hardware, so a handful of
+  // retries covers every wait of a healthy pipeline); the watchdog loop lives out of line to keep hot code small
+#pragma unroll 1
+  for (int i = 0; i < 32; ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 
 // generic-proxy smem writes -> visible to the async proxy (tensor core / TMA reads)
