@@ -91,7 +91,7 @@ __host__ __device__ inline size_t tc_weight_bytes(const TcArgs& a) {
   return s;
 }
 __host__ __device__ inline size_t tc_stage_bytes(const TcArgs& a) { return ((size_t)kTcTileM * a.in_dim * 4 + 127) & ~(size_t)127; }
-__host__ __device__ inline size_t tc_smem_bytes(const TcArgs& a) { return tc_weight_bytes(a) + 2 * tc_stage_bytes(a) + 128; }
+__host__ __device__ inline size_t tc_smem_bytes(const TcArgs& a) { return tc_weight_bytes(a) + 2 * tc_stage_bytes(a) + 256; }
 
 // ELU in the base-2 domain on 32 accumulator columns -> 16 words of packed 16-bit operands.
 //   e = 2^z' (MUFU), f = c*e - c (FFMA), result = z' < 0 ? f : z' selected on the packed pair.
@@ -219,15 +219,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const TcArgs a) {
   uint64_t* obs_empty = bars + 2;   // [2]
   uint64_t* acc_full = bars + 4;    // [2]
   uint64_t* a_blk = bars + 6;       // [2][4]  A operand of the next layer ready, per 32-column block
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* w_full = bars + 14;     // [kMaxLayers]  layer weights landed in shared memory (completes once)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14 + kMaxLayers);
 
-  // ---- one-time setup: weights -> smem, barriers, TMEM
-  {
-    const int4* src = reinterpret_cast<const int4*>(a.wpack);
-    int4* dst = reinterpret_cast<int4*>(w_smem);
-    const int n16 = (int)(wbytes >> 4);
-    for (int i = tid; i < n16; i += kTcThreads) dst[i] = src[i];
-  }
+  // ---- one-time setup: barriers, TMEM; the weights arrive as one bulk async copy per layer, each with its own
+  // mbarrier, so the first tile's conversion and layer-0 MMA do not wait for the deeper layers' weights (matters for
+  // small batches, where a CTA sees a single tile)
   if (warp == kTcCtrlWarp0) {
     if (lane == 0) {
       for (int s = 0; s < 2; ++s) {
@@ -235,12 +232,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const TcArgs a) {
         ptx::mbar_init(&acc_full[s], 1);
         for (int b = 0; b < kTcBlocks; ++b) ptx::mbar_init(&a_blk[s * kTcBlocks + b], 4);   // 4 lane quarters
       }
+      for (int l = 0; l < a.n_layers; ++l) ptx::mbar_init(&w_full[l], 1);
       ptx::fence_mbar_init();
+      uint32_t off = 0;
+      for (int l = 0; l < a.n_layers; ++l) {
+        const uint32_t bytes = (uint32_t)(tc_layer_kp(a, l) * tc_layer_n(a, l) * 2);
+        ptx::mbar_arrive_expect_tx(&w_full[l], bytes);
+        ptx::bulk_g2s(w_smem + off, reinterpret_cast<const uint8_t*>(a.wpack) + off, bytes, &w_full[l]);
+        off += bytes;
+      }
     }
     __syncwarp();
     ptx::tmem_alloc<512>(tmem_ptr);
   }
-  ptx::fence_proxy_async_smem();   // weights were written through the generic proxy; UMMA reads via the async proxy
   ptx::tc_fence_before();
   block_sync();
   ptx::tc_fence_after();
@@ -288,6 +292,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const TcArgs a) {
         const uint64_t bdesc0 = ptx::make_smem_desc_nosw(w_base + w_off, 128u, (uint32_t)kp * 16u);
         const uint32_t src = tmem_base + (uint32_t)s * kTcSlotCols + 128u * (uint32_t)((phi + l) & 1);
         const uint32_t dst = tmem_base + (uint32_t)s * kTcSlotCols + 128u * (uint32_t)((phi + l + 1) & 1);
+        ptx::mbar_wait(&w_full[l], 0u);      // completes once; later waits return at the first probe
         if (l == 0) {
           for (int q = 0; q < kTcBlocks; ++q) ptx::mbar_wait(&blk[q], par);
           ptx::tc_fence_after();
