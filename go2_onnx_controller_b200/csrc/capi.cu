@@ -236,10 +236,18 @@ int upload_model(go2p_handle* h) {
   return GO2P_OK;
 }
 
+// the Go2 topology keeps its weights in registers (kernels_b1.cuh: B1RegWeights)
+bool b1_regs_ok(const go2p_handle* h) {
+  const DevModel& m = h->dm;
+  return m.n_layers == 4 && m.L[0].N == 128 && m.L[1].N == 128 && m.L[2].N == 128 && m.L[1].K == 128 && m.L[2].K == 128 &&
+         m.L[3].K == 128 && m.L[3].N <= 16 && m.L[0].Kp <= 112 && std::getenv("GO2P_B1_NO_REGS") == nullptr;
+}
+
 size_t b1_smem_bytes(const go2p_handle* h, bool resident, bool* weights_fit) {
   const int XW = b1_xw(std::max(h->dm.max_width, h->n_in_slots));
   size_t bytes = (size_t)(2 * XW + kB1Threads + 64) * 4;
   *weights_fit = false;
+  if (resident && b1_regs_ok(h)) return bytes + sizeof(B1State) + 4 * 128 * 4;
   if (resident) {
     bytes += sizeof(B1State);
     size_t w = 0;
@@ -608,10 +616,13 @@ int go2p_persistent_start(go2p_handle* h) {
   DeviceGuard g(h->device);
   bool fit = false;
   const size_t smem = b1_smem_bytes(h, true, &fit);
-  CU_TRY(cudaFuncSetAttribute(b1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool regs = b1_regs_ok(h);
+  if (regs) CU_TRY(cudaFuncSetAttribute(b1_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else CU_TRY(cudaFuncSetAttribute(b1_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ++h->epoch;
   B1Args a = make_b1_args(h, fit);
-  b1_kernel<true><<<1, kB1Threads, smem, h->b1_stream>>>(a);
+  if (regs) b1_kernel<true, true><<<1, kB1Threads, smem, h->b1_stream>>>(a);
+  else b1_kernel<true, false><<<1, kB1Threads, smem, h->b1_stream>>>(a);
   CU_TRY(cudaGetLastError());
   h->resident = true;
   h->b1_smem = smem;
@@ -726,7 +737,8 @@ int go2p_b1_selfdriven(go2p_handle* h, const go2p_raw_state* raws, int n_raws, i
   DeviceGuard g(h->device);
   bool fit = false;
   const size_t smem = b1_smem_bytes(h, true, &fit);
-  if (!fit) return fail(GO2P_ERR_UNSUPPORTED, "weights do not fit shared memory");
+  const bool regs = b1_regs_ok(h);
+  if (!fit && !regs) return fail(GO2P_ERR_UNSUPPORTED, "weights fit neither the register file nor shared memory");
   std::vector<uint32_t> words((size_t)n_raws * kRawWords);
   for (int r = 0; r < n_raws; ++r) {
     uint32_t* w = &words[(size_t)r * kRawWords];
@@ -746,14 +758,16 @@ int go2p_b1_selfdriven(go2p_handle* h, const go2p_raw_state* raws, int n_raws, i
   init.kp = h->cfg.kp; init.kd = h->cfg.kd;
   CU_TRY(cudaMemcpy(d_st, &init, sizeof(init), cudaMemcpyHostToDevice));
   CU_TRY(cudaMemcpy(d_raws, words.data(), words.size() * 4, cudaMemcpyHostToDevice));
-  CU_TRY(cudaFuncSetAttribute(b1_selfdriven_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (regs) CU_TRY(cudaFuncSetAttribute(b1_selfdriven_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else CU_TRY(cudaFuncSetAttribute(b1_selfdriven_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   B1Args a = make_b1_args(h, true);
   a.gstate = d_st;
   cudaEvent_t e0, e1;
   CU_TRY(cudaEventCreate(&e0));
   CU_TRY(cudaEventCreate(&e1));
   CU_TRY(cudaEventRecord(e0, h->pipe_stream[0]));
-  b1_selfdriven_kernel<<<1, kB1Threads, smem, h->pipe_stream[0]>>>(a, d_raws, n_raws, steps, d_out);
+  if (regs) b1_selfdriven_kernel<true><<<1, kB1Threads, smem, h->pipe_stream[0]>>>(a, d_raws, n_raws, steps, d_out);
+  else b1_selfdriven_kernel<false><<<1, kB1Threads, smem, h->pipe_stream[0]>>>(a, d_raws, n_raws, steps, d_out);
   CU_TRY(cudaGetLastError());
   CU_TRY(cudaEventRecord(e1, h->pipe_stream[0]));
   CU_TRY(cudaEventSynchronize(e1));

@@ -235,11 +235,81 @@ __device__ __forceinline__ void b1_layer_n128(const float4* __restrict__ w4, con
   block_sync();
 }
 
+// Register-resident weights for the Go2 topology (4 layers, hidden width 128, K0 <= 112, out <= 16): the 47 k fp32
+// weights fit in the register file of one 512-thread CTA (96 per thread), so a control step reads no weight from
+// shared memory at all -- only the 128-float activation vector, as warp-uniform (broadcast) float4 loads.
+// Thread mapping for the hidden layers: warp w -> K-group g = w & 3, output block w >> 2; lane -> output inside the
+// block.  K slices, accumulator interleave and the order in which the four partial sums are combined are exactly
+// those of b1_layer_n128 / b1_layer, so all batch-1 variants produce identical bits.
+struct B1RegWeights {
+  float4 w0[7], w1[8], w2[8], w3;
+
+  __device__ __forceinline__ static bool supported(const DevModel& m) {
+    return m.n_layers == 4 && m.L[0].N == 128 && m.L[1].N == 128 && m.L[2].N == 128 && m.L[1].K == 128 && m.L[2].K == 128 &&
+           m.L[3].K == 128 && m.L[3].N <= 16 && m.L[0].Kp <= 112;
+  }
+  __device__ __forceinline__ void load(const DevModel& m, int tid) {
+    const int warp = tid >> 5, lane = tid & 31, g = warp & 3, o = (warp >> 2) * 32 + lane;
+    const int K4_0 = m.L[0].Kp >> 2;
+    const float4* s0 = reinterpret_cast<const float4*>(m.L[0].w_k4);
+    const float4* s1 = reinterpret_cast<const float4*>(m.L[1].w_k4);
+    const float4* s2 = reinterpret_cast<const float4*>(m.L[2].w_k4);
+#pragma unroll
+    for (int j = 0; j < 7; ++j) { const int k4 = g * 7 + j; w0[j] = (k4 < K4_0) ? s0[k4 * 128 + o] : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { w1[j] = s1[(g * 8 + j) * 128 + o]; w2[j] = s2[(g * 8 + j) * 128 + o]; }
+    w3 = (warp < m.L[3].N) ? reinterpret_cast<const float4*>(m.L[3].w_rm + (size_t)warp * m.L[3].Kp)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  template <int kSteps>
+  __device__ __forceinline__ static void hidden(const float4 (&w)[kSteps], const float* __restrict__ bias, bool has_elu, float alpha,
+                                                const float* __restrict__ x, float* __restrict__ y, float* __restrict__ part, int tid) {
+    const int warp = tid >> 5, lane = tid & 31, g = warp & 3, o = (warp >> 2) * 32 + lane;
+    const float4* x4 = reinterpret_cast<const float4*>(x) + g * kSteps;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kSteps; ++j) {
+      const float4 xv = x4[j];
+      a0 = fmaf(w[j].x, xv.x, a0); a1 = fmaf(w[j].y, xv.y, a1); a2 = fmaf(w[j].z, xv.z, a2); a3 = fmaf(w[j].w, xv.w, a3);
+    }
+    part[g * 128 + o] = (a0 + a1) + (a2 + a3);
+    block_sync();
+    if (tid < 128) {
+      float s = (part[tid] + part[128 + tid]) + (part[256 + tid] + part[384 + tid]);
+      s += bias[tid];
+      if (has_elu) s = (s < 0.0f) ? alpha * (__expf(s) - 1.0f) : s;
+      y[tid] = s;
+    }
+    block_sync();
+  }
+  // xa: layer-0 input zero padded to 112 floats.  Returns the buffer holding the policy output.
+  __device__ __forceinline__ float* forward(const DevModel& m, const float* __restrict__ bsm, float* xa, float* xb, float* part, int tid) const {
+    hidden<7>(w0, bsm, m.L[0].has_elu != 0, m.L[0].alpha, xa, xb, part, tid);
+    hidden<8>(w1, bsm + 128, m.L[1].has_elu != 0, m.L[1].alpha, xb, xa, part, tid);
+    hidden<8>(w2, bsm + 256, m.L[2].has_elu != 0, m.L[2].alpha, xa, xb, part, tid);
+    const int warp = tid >> 5, lane = tid & 31;
+    if (warp < ((m.L[3].N + 3) & ~3)) {
+      float s = 0.f;
+      if (warp < m.L[3].N) {
+        const float4 xv = reinterpret_cast<const float4*>(xb)[lane];
+        float acc = 0.f;
+        acc = fmaf(w3.x, xv.x, acc); acc = fmaf(w3.y, xv.y, acc); acc = fmaf(w3.z, xv.z, acc); acc = fmaf(w3.w, xv.w, acc);
+        acc = warp_sum(acc);
+        s = acc + bsm[384 + warp];
+        if (m.L[3].has_elu) s = elu_exact(s, m.L[3].alpha);
+      }
+      if (lane == 0) xa[warp] = s;
+    }
+    block_sync();
+    return xa;
+  }
+};
+
 // Dynamic shared memory layout (floats): xa[XW] xb[XW] part[kB1Threads] raw[64] state weights...
 __host__ __device__ inline int b1_xw(int max_width) { return ((max_width + 3) & ~3) + 4; }
 
-template <bool kResident>
+template <bool kResident, bool kRegs = false>
 __global__ void __launch_bounds__(kB1Threads, 1) b1_kernel(const B1Args a) {
+  static_assert(kResident || !kRegs, "register-resident weights only make sense for the resident kernel");
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x;
   const int XW = b1_xw(a.model.max_width);
@@ -259,7 +329,15 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_kernel(const B1Args a) {
       reinterpret_cast<uint32_t*>(sst)[i] = reinterpret_cast<const uint32_t*>(a.gstate)[i];
     st = sst;
     if (tid == 0) s_quit = 0;
-    if (a.weights_in_smem) {
+    if (kRegs) {
+      // biases of the four layers, 128 floats each (zero padded), right behind the state
+      float* b = reinterpret_cast<float*>(sst + 1);
+      for (int i = tid; i < 4 * 128; i += kB1Threads) {
+        const DevLayer& L = a.model.L[i >> 7];
+        b[i] = ((i & 127) < L.N) ? L.bias[i & 127] : 0.f;
+      }
+      wsm = b;
+    } else if (a.weights_in_smem) {
       // weights (in the layout each layer reads) and biases become shared-memory resident for the
       // life of the kernel: a control step touches no global/HBM weight byte.
       float* w = reinterpret_cast<float*>(sst + 1);
@@ -279,6 +357,9 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_kernel(const B1Args a) {
     }
     block_sync();
   }
+
+  B1RegWeights regw;
+  if (kRegs) regw.load(a.model, tid);
 
   const int H = a.cc.H;
   const int n_obs = kFrame * H;
@@ -381,14 +462,15 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_kernel(const B1Args a) {
       }
     }
     // zero the K padding of the first layer input
-    if (tid >= a.model.in_dim && tid < a.model.L[0].Kp) xa[tid] = 0.f;
+    if (tid >= a.model.in_dim && tid < (kRegs ? 112 : a.model.L[0].Kp)) xa[tid] = 0.f;
     block_sync();
 
     // ---- A7: Gemm/Elu chain
     float* x = xa;
     float* y = xb;
     int woff = 0;
-    for (int l = 0; l < a.model.n_layers; ++l) {
+    if (kRegs) x = regw.forward(a.model, wsm, xa, xb, part, tid);
+    else for (int l = 0; l < a.model.n_layers; ++l) {
       const DevLayer& L = a.model.L[l];
       const float* wk4 = L.w_k4; const float* wrm = L.w_rm; const float* bias = L.bias;
       if (kResident && wsm) {
@@ -454,6 +536,7 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_kernel(const B1Args a) {
 // Bounded, self-driven variant for profilers: runs `steps` closed-loop steps on raw states read
 // from device memory (cycled), no mailbox -- lets ncu report per-step DRAM bytes of the resident
 // design (a kernel that never exits cannot be profiled).  Same device functions as b1_kernel.
+template <bool kRegs>
 __global__ void __launch_bounds__(kB1Threads, 1) b1_selfdriven_kernel(const B1Args a, const uint32_t* __restrict__ raws,
                                                                       int n_raws, int steps, float* __restrict__ out_actions) {
   extern __shared__ __align__(16) float sm[];
@@ -465,7 +548,14 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_selfdriven_kernel(const B1Ar
   for (int i = tid; i < (int)(sizeof(B1State) / 4); i += kB1Threads)
     reinterpret_cast<uint32_t*>(st)[i] = reinterpret_cast<const uint32_t*>(a.gstate)[i];
   float* w = reinterpret_cast<float*>(st + 1);
-  {
+  B1RegWeights regw;
+  if (kRegs) {
+    regw.load(a.model, tid);
+    for (int i = tid; i < 4 * 128; i += kB1Threads) {
+      const DevLayer& L = a.model.L[i >> 7];
+      w[i] = ((i & 127) < L.N) ? L.bias[i & 127] : 0.f;
+    }
+  } else {
     int off = 0;
     for (int l = 0; l < a.model.n_layers; ++l) {
       const DevLayer& L = a.model.L[l];
@@ -501,10 +591,11 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_selfdriven_kernel(const B1Ar
     if (tid < n_obs) v = newest ? part[frame_offset(t) + c] : st->obs[tid + wdt];
     block_sync();
     if (tid < n_obs) { st->obs[tid] = v; xa[tid] = v; if (newest && t == 2) st->vel_cmd[c] = v; }
-    if (tid >= a.model.in_dim && tid < a.model.L[0].Kp) xa[tid] = 0.f;
+    if (tid >= a.model.in_dim && tid < (kRegs ? 112 : a.model.L[0].Kp)) xa[tid] = 0.f;
     block_sync();
     float* x = xa; float* y = xb; int woff = 0;
-    for (int l = 0; l < a.model.n_layers; ++l) {
+    if (kRegs) x = regw.forward(a.model, w, xa, xb, part, tid);
+    else for (int l = 0; l < a.model.n_layers; ++l) {
       const DevLayer& L = a.model.L[l];
       const float* wl = w + woff;
       if (L.N == 128) b1_layer_n128(reinterpret_cast<const float4*>(wl), wl + L.Kp * L.N, L.Kp >> 2, L.has_elu != 0, L.alpha,
