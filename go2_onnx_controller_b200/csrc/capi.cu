@@ -252,7 +252,7 @@ size_t b1_smem_bytes(const go2p_handle* h, bool resident, bool* weights_fit) {
     bytes += sizeof(B1State);
     size_t w = 0;
     for (int l = 0; l < h->dm.n_layers; ++l) w += (size_t)h->dm.L[l].Kp * h->dm.L[l].N + round_up(h->dm.L[l].N, 4);
-    if (bytes + w * 4 <= 227 * 1024) { bytes += w * 4; *weights_fit = true; }
+    if (bytes + w * 4 <= 226 * 1024) { bytes += w * 4; *weights_fit = true; }   // 1 KB left for static shared memory
   }
   return bytes;
 }

@@ -397,6 +397,49 @@ def test_resident_kernel_coexists_with_batched_kernels(torch_cuda, model_path, g
         p.close()
 
 
+@pytest.mark.parametrize("shape", [
+    dict(dims=(77, 128, 128, 7), alpha=0.5, final_act=False),        # odd input width, 3 layers, 7 outputs
+    dict(dims=(64, 128, 12), alpha=1.0, final_act=True),             # 2 layers, ELU on the output layer too
+    dict(dims=(40, 128, 128, 128, 128, 16), alpha=1.3, final_act=False),    # 5 layers, widest output the TC kernel serves
+])
+def test_other_narrow_policies_all_paths(torch_cuda, tmp_path, shape):
+    """The kernels are driven by the parsed graph, not by the bundled policy's constants: other layer counts, input
+    widths (odd: scalar conversion path), output widths (generic output epilogue), ELU alphas and an activation on the
+    last layer (scaled-domain output) must agree with the oracle on every path that serves them."""
+    from oracle import onnx_mini
+    dims = shape["dims"]
+    rng = np.random.default_rng(sum(dims))
+    ws = [rng.normal(0, 1.0 / np.sqrt(k), (n, k)).astype(np.float32) for k, n in zip(dims[:-1], dims[1:])]
+    bs = [rng.normal(0, 0.2, n).astype(np.float32) for n in dims[1:]]
+    path = tmp_path / "m.onnx"
+    path.write_bytes(onnx_mini.write_mlp_onnx(ws, bs, shape["alpha"], final_activation=shape["final_act"]))
+    cm = coracle.CModel(str(path))
+    p = PolicyBatch(str(path))
+    try:
+        assert p.info.tensor_core_path == 1
+        for B in (1, 129, 1000):
+            X = rng.normal(0, 1, (B, dims[0])).astype(np.float32)
+            ref = cm.forward_f64(X, 4)
+            y, _ = run_batch(torch_cuda, p, X, capi.PREC_FP32)
+            assert_fp32_parity(y.astype(np.float64), ref)
+            y, _ = run_batch(torch_cuda, p, X, capi.PREC_FP16)
+            assert np.abs(y - ref).max() <= 3e-2, np.abs(y - ref).max()
+            y, _ = run_batch(torch_cuda, p, X, capi.PREC_BF16)
+            assert np.abs(y - ref).max() <= 1.5e-1, np.abs(y - ref).max()
+        # batch-1 act() on the same graph (generic kernel: weights in shared memory)
+        obs, act = np.zeros(dims[0], np.float32), np.zeros(dims[-1], np.float32)
+        a = ONNXActor(str(path), obs, act)
+        try:
+            for i in range(5):
+                obs[:] = X[i]
+                a.act()
+                assert_fp32_parity(act.astype(np.float64), ref[i])
+        finally:
+            a.close()
+    finally:
+        p.close()
+
+
 def test_wide_policy_fp32_path(torch_cuda, wide_model_path):
     """BASELINE.json configs[4]: synthetic 245-1024-512-256-12 ELU policy (5-frame history input)."""
     cm = coracle.CModel(wide_model_path)
