@@ -578,6 +578,7 @@ int go2p_destroy(go2p_handle* h) {
   }
   if (h->b1_stream) cudaStreamDestroy(h->b1_stream);
   for (void* p : h->dev_owned) cudaFree(p);
+  wide_release(&h->wide);
   for (auto& sc : h->scratch_sets)
     for (int i = 0; i < 2; ++i) if (sc.buf[i]) cudaFree(sc.buf[i]);
   if (h->d_state) cudaFree(h->d_state);
@@ -822,11 +823,9 @@ int go2p_infer_batch_ex(go2p_handle* h, const float* d_obs, const int32_t* d_but
     case GO2P_PREC_FP16:
       if (h->tc_ok) return launch_tc(h, d_obs, d_button0, d_act, d_qdes, B, precision == GO2P_PREC_FP16, flags, st);
       if (h->wide_ok) {
-        int rc = ensure_scratch(h, std::min<int64_t>(B, kFp32ChunkRows));
-        if (rc) return rc;
-        rc = wide_launch(h->wide, d_obs, d_button0, d_act, d_qdes, B, precision == GO2P_PREC_FP16, flags, h->cc,
-                         h->sm_count, st, &h->last_launches, g_err);
-        return rc;
+        int rc = wide_launch(h->wide, d_obs, d_button0, d_act, d_qdes, B, precision == GO2P_PREC_FP16, flags, h->cc,
+                             h->sm_count, st, &h->last_launches, g_err, h->scratch_sel);
+        return rc ? fail(rc, g_err.c_str()) : GO2P_OK;
       }
       return fail(GO2P_ERR_UNSUPPORTED, "tensor-core kernels do not serve this layer shape; use GO2P_PREC_FP32");
     case GO2P_PREC_TF32:

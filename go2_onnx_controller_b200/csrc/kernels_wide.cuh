@@ -1,15 +1,389 @@
-// placeholder until the wide-layer tcgen05 kernel lands: reports "shape not served"
+// Batched forward for policies whose layers are too wide for the all-in-shared-memory kernel (kernels_tc.cuh), e.g.
+// BASELINE.json configs[4]: 245 -> 1024 -> 512 -> 256 -> 12 with a 5-frame observation history.
+//
+//   A7  Gemm/Elu chain   reference: onnx_actor.cpp:38-48 (Ort::Session::Run), one tcgen05 GEMM launch per layer
+//   A9/A11 epilogue      reference: controller.cpp:217-223,244 (fused into the last layer's epilogue)
+//
+// Design:
+//   * activations travel between layers as 16-bit values in a TILE-BLOCKED layout in global memory (they stay L2
+//     resident for the chunk sizes the host uses): tiles of 128 rows x 64 K-columns, each tile stored exactly as the
+//     UMMA K-major no-swizzle core-matrix image the tensor core reads from shared memory (8x8-element cores of 128
+//     contiguous bytes, K-adjacent cores contiguous, 8-row groups 1024 B apart).  A tile is therefore ONE contiguous
+//     16 KB chunk: a single 1-D bulk async copy (TMA engine) brings it in, no tensor map and no relayout;
+//   * weights are packed on the host the same way per (N-tile, K-chunk);
+//   * wide_gemm_kernel: persistent CTAs over (row tile, N tile); warp 0 = producer (3-stage mbarrier ring of A/B
+//     chunks), warp 1 = MMA issuer (SS-form tcgen05.mma, M=128, N=NT, four K steps per 64-wide chunk, accumulators
+//     double-buffered in TMEM so the epilogue of one tile overlaps the MMAs of the next), warps 2-5 = epilogue
+//     (tcgen05.ld -> +bias -> ELU -> 16-bit -> blocked store for the next layer, or the fused A9/A11 output epilogue);
+//   * obs_to_blocked_kernel converts the fp32 [B,in] observations into the blocked 16-bit layout (zero padded).
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include <string>
 #include <vector>
+
 #include "onnx_reader.hpp"
 #include "policy_dev.cuh"
+#include "ptx_sm100.cuh"
+
 namespace go2p {
-struct WideModel { int n_layers = 0; };
-inline int wide_prepare(const MlpModel&, std::vector<void*>&, WideModel*, std::string&) { return -1; }
-inline int wide_launch(const WideModel&, const float*, const int32_t*, float*, double*, long long, bool, uint32_t,
-                       const CtrlConst&, int, cudaStream_t, int*, std::string& err) {
-  err = "wide tensor-core path not built";
-  return 6;
+
+constexpr int kWdTileM = 128;
+constexpr int kWdChunkK = 64;                       // K columns per pipeline stage (4 MMA K steps)
+constexpr int kWdATileBytes = kWdTileM * kWdChunkK * 2;   // 16 KB
+constexpr int kWdStages = 3;
+constexpr int kWdThreads = 6 * 32;                  // producer, MMA issuer, 4 epilogue warps
+
+// byte offset of element (r, c) inside a [rows x 64] blocked tile (rows multiple of 8)
+__host__ __device__ inline uint32_t wd_tile_offset(int r, int c) {
+  return (uint32_t)(((r >> 3) * 8 + (c >> 3)) * 128 + (r & 7) * 16 + (c & 7) * 2);
 }
+
+struct WideLayerDev {
+  const uint16_t* w[2];    // [0] bf16, [1] fp16: per (n tile, k chunk) blocked image, NT rows x 64
+  const float* bias;       // [Npad]
+  int K, N, Kp, Np, NT;    // Kp multiple of 64, Np multiple of NT
+  int has_elu;
+  float alpha;
+};
+
+struct WideModel {
+  int n_layers = 0;
+  int in_dim = 0, out_dim = 0;
+  WideLayerDev L[kMaxLayers];
+  int max_kp = 0;          // widest blocked activation (in K columns)
+  // activation ping-pong buffers (allocated lazily by wide_launch for a chunk of rows)
+  // one pair per stream set (capi.cu: scratch_sel; the host-buffer pipeline runs several streams concurrently)
+  static constexpr int kSets = 4;
+  mutable uint16_t* act[kSets][2] = {};
+  mutable long long act_rows[kSets] = {};
+};
+
+struct WideGemmArgs {
+  const uint16_t* a;        // blocked activations [Mp/128][Kp/64] tiles
+  const uint16_t* w;        // blocked weights     [Np/NT][Kp/64] tiles
+  const float* bias;
+  uint16_t* out_blocked;    // next layer's blocked activations (Kp_next = Np), or null for the output layer
+  float* out_rows;          // [M, out_dim] fp32 (output layer)
+  const int32_t* button0;
+  double* qdes;
+  long long M;              // valid rows
+  int m_tiles, n_tiles, k_chunks;
+  int N, out_dim, has_elu;
+  float alpha;
+  uint32_t flags;
+  float action_limit;
+  double action_scale;
+  double q0[kDof];
+};
+
+// fp32 [B, in] row-major -> blocked 16-bit tiles, zero padded to (m_tiles*128) x Kp
+template <bool kFp16>
+__global__ void obs_to_blocked_kernel(const float* __restrict__ obs, uint16_t* __restrict__ out, long long B, int in_dim, int Kp,
+                                      long long m_tiles) {
+  const long long groups = m_tiles * kWdTileM * (Kp / 8);          // one thread per (row, 8-column group)
+  for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < groups; gidx += (long long)gridDim.x * blockDim.x) {
+    const int kg = (int)(gidx % (Kp / 8));
+    const long long row = gidx / (Kp / 8);
+    uint32_t p[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = kg * 8 + 2 * j;
+      const float lo = (row < B && k < in_dim) ? obs[row * in_dim + k] : 0.f;
+      const float hi = (row < B && k + 1 < in_dim) ? obs[row * in_dim + k + 1] : 0.f;
+      p[j] = kFp16 ? ptx::pack_f16_sat(lo, hi) : ptx::pack_bf16(lo, hi);
+    }
+    const long long mt = row / kWdTileM;
+    const int r = (int)(row % kWdTileM);
+    const int kc = (kg * 8) / kWdChunkK, c = (kg * 8) % kWdChunkK;
+    uint8_t* dst = reinterpret_cast<uint8_t*>(out) + ((mt * (Kp / kWdChunkK) + kc) * (long long)kWdATileBytes) + wd_tile_offset(r, c);
+    *reinterpret_cast<uint4*>(dst) = make_uint4(p[0], p[1], p[2], p[3]);
+  }
+}
+
+template <int NT, bool kFp16>
+__global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemmArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int kBTileBytes = NT * kWdChunkK * 2;
+  constexpr int kStageBytes = kWdATileBytes + kBTileBytes;
+  constexpr uint32_t kAccCols = NT < 32 ? 32 : NT;               // TMEM columns per accumulator buffer
+  constexpr uint32_t kTmemCols = 2 * kAccCols;                   // 64 .. 512, a power of two
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWdStages * kStageBytes);
+  uint64_t* full = bars;                 // [kWdStages] chunk landed
+  uint64_t* empty = bars + kWdStages;    // [kWdStages] chunk consumed by the tensor core
+  uint64_t* acc_full = bars + 2 * kWdStages;       // [2]
+  uint64_t* acc_empty = bars + 2 * kWdStages + 2;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kWdStages + 4);
+
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kWdStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+      for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], 4); }
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc<kTmemCols>(tmem_ptr);
+  }
+  ptx::tc_fence_before();
+  block_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const long long n_jobs = (long long)a.m_tiles * a.n_tiles;     // job = (row tile, N tile), N tile fastest: A stays in L2
+  if (warp == 0) {
+    // ================= producer =================
+    uint32_t it = 0;
+    for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+      const long long mt = job / a.n_tiles;
+      const int nt = (int)(job % a.n_tiles);
+      for (int kc = 0; kc < a.k_chunks; ++kc, ++it) {
+        const int s = it % kWdStages;
+        ptx::mbar_wait(&empty[s], ((it / kWdStages) & 1u) ^ 1u);
+        if (ptx::elect_one_sync()) {
+          uint8_t* st = smem + s * kStageBytes;
+          ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)kStageBytes);
+          ptx::bulk_g2s(st, reinterpret_cast<const uint8_t*>(a.a) + (mt * a.k_chunks + kc) * (long long)kWdATileBytes, kWdATileBytes, &full[s]);
+          ptx::bulk_g2s(st + kWdATileBytes, reinterpret_cast<const uint8_t*>(a.w) + ((long long)nt * a.k_chunks + kc) * (long long)kBTileBytes,
+                        kBTileBytes, &full[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    const uint32_t idesc = ptx::make_idesc(kFp16 ? ptx::FMT_F16 : ptx::FMT_BF16, kWdTileM, (uint32_t)NT);
+    uint32_t it = 0, tile_i = 0;
+    for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x, ++tile_i) {
+      const uint32_t buf = tile_i & 1u;
+      ptx::mbar_wait(&acc_empty[buf], ((tile_i >> 1) & 1u) ^ 1u);
+      ptx::tc_fence_after();
+      const uint32_t d_t = tmem_base + buf * kAccCols;
+      for (int kc = 0; kc < a.k_chunks; ++kc, ++it) {
+        const int s = it % kWdStages;
+        ptx::mbar_wait(&full[s], (it / kWdStages) & 1u);
+        ptx::tc_fence_after();
+        if (ptx::elect_one_sync()) {
+          const uint32_t sa = ptx::smem_u32(smem + s * kStageBytes);
+          const uint64_t adesc = ptx::make_smem_desc_nosw(sa, 128u, 1024u);
+          const uint64_t bdesc = ptx::make_smem_desc_nosw(sa + kWdATileBytes, 128u, 1024u);
+#pragma unroll
+          for (int j = 0; j < kWdChunkK / 16; ++j)
+            ptx::mma_f16_ss(d_t, adesc + (uint64_t)(j * 16), bdesc + (uint64_t)(j * 16), idesc, (kc | j) ? 1u : 0u);
+          ptx::mma_commit(&empty[s]);                       // frees the stage when these MMAs have read it
+          if (kc == a.k_chunks - 1) ptx::mma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================= epilogue warps (lane quarter = warp % 4) =================
+    const int quarter = warp & 3;
+    const uint32_t lane_addr = ((uint32_t)(quarter * 32)) << 16;
+    const int r = quarter * 32 + lane;               // row inside the tile
+    uint32_t tile_i = 0;
+    for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x, ++tile_i) {
+      const long long mt = job / a.n_tiles;
+      const int nt = (int)(job % a.n_tiles);
+      const uint32_t buf = tile_i & 1u;
+      ptx::mbar_wait(&acc_full[buf], (tile_i >> 1) & 1u);
+      ptx::tc_fence_after();
+      const uint32_t acc_t = tmem_base + buf * kAccCols + lane_addr;
+      const long long row = mt * kWdTileM + r;
+      if (a.out_blocked) {
+        // hidden layer: 32 columns at a time -> bias + ELU -> 16 bit -> four 16-byte stores into the next layer's tile
+        const int kcn_per_tile = NT / kWdChunkK;       // 64-column chunks of the next layer covered by this N tile
+        const long long next_chunks = (long long)a.n_tiles * kcn_per_tile;
+#pragma unroll 1
+        for (int c0 = 0; c0 < NT; c0 += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld_x32(acc_t + (uint32_t)c0, v);
+          ptx::tc_wait_ld();
+          const float* bl = a.bias + nt * NT + c0;
+          uint32_t p[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float x0 = __uint_as_float(v[2 * j]) + bl[2 * j];
+            float x1 = __uint_as_float(v[2 * j + 1]) + bl[2 * j + 1];
+            if (a.has_elu) {
+              const float e0 = fmaf(a.alpha, ptx::ex2_approx(x0 * 1.4426950408889634f), -a.alpha);
+              const float e1 = fmaf(a.alpha, ptx::ex2_approx(x1 * 1.4426950408889634f), -a.alpha);
+              x0 = (x0 < 0.f) ? e0 : x0;
+              x1 = (x1 < 0.f) ? e1 : x1;
+            }
+            p[j] = kFp16 ? ptx::pack_f16_sat(x0, x1) : ptx::pack_bf16(x0, x1);
+          }
+          const int kn = nt * NT + c0;                 // K index of the next layer
+          uint8_t* dst = reinterpret_cast<uint8_t*>(a.out_blocked) + ((mt * next_chunks + kn / kWdChunkK) * (long long)kWdATileBytes) +
+                         wd_tile_offset(r, kn % kWdChunkK);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)                  // consecutive 8-column cores are 128 B apart inside the tile
+            *reinterpret_cast<uint4*>(dst + q * 128) = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+        }
+      } else {
+        // output layer (NT == 16): bias (+ELU) (+clamp/mask) (+q_des) -> fp32 rows
+        uint32_t v[16];
+        ptx::tmem_ld_x16(acc_t, v);
+        ptx::tc_wait_ld();
+        if (row < a.M) {
+          const int b0 = ((a.flags & 1u) && a.button0) ? a.button0[row] : 0;
+          float* dst = a.out_rows + row * a.out_dim;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (j < a.out_dim) {
+              float x = __uint_as_float(v[j]) + a.bias[j];
+              if (a.has_elu) x = (x < 0.f) ? fmaf(a.alpha, ptx::ex2_approx(x * 1.4426950408889634f), -a.alpha) : x;
+              if (a.flags & 1u) x = clamp_mask(x, a.action_limit, b0);
+              dst[j] = x;
+              if ((a.flags & 2u) && a.qdes && j < kDof) a.qdes[row * kDof + j] = joint_target(x, a.q0[j], a.action_scale);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  block_sync();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+inline int wd_round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// blocked image of W [N][K] for N tiles of NT rows: tile (nt, kc) = NT x 64 elements
+inline void wd_pack_weights(const MlpLayer& L, int NT, int Np, int Kp, bool fp16, std::vector<uint16_t>& out) {
+  out.assign((size_t)Np * Kp, 0);
+  const int k_chunks = Kp / kWdChunkK;
+  for (int n = 0; n < L.out; ++n)
+    for (int k = 0; k < L.in; ++k) {
+      const float v = L.weight[(size_t)n * L.in + k];
+      const size_t tile = ((size_t)(n / NT) * k_chunks + k / kWdChunkK) * ((size_t)NT * kWdChunkK);
+      const size_t idx = tile + wd_tile_offset(n % NT, k % kWdChunkK) / 2;
+      uint16_t b;
+      if (fp16) { const float c = v > 65504.f ? 65504.f : (v < -65504.f ? -65504.f : v); b = __half_as_ushort(__float2half_rn(c)); }
+      else b = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+      out[idx] = b;
+    }
+}
+
+// returns 0 = ok, > 0 = go2p_status (CUDA failure), < 0 = this shape is not served by the wide path
+inline int wide_prepare(const MlpModel& m, std::vector<void*>& dev_owned, WideModel* wm, std::string& err) {
+  const int nl = (int)m.layers.size();
+  if (nl < 2 || nl > kMaxLayers || m.layers.back().out > 16) return -1;
+  for (int l = 0; l + 1 < nl; ++l) if (m.layers[l].out % 64 != 0) return -1;
+  wm->n_layers = nl; wm->in_dim = m.layers.front().in; wm->out_dim = m.layers.back().out; wm->max_kp = 0;
+  auto upload = [&](const void* src, size_t bytes, void** out) -> bool {
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { err = "wide_prepare: cudaMalloc failed"; return false; }
+    dev_owned.push_back(p);
+    if (cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { err = "wide_prepare: cudaMemcpy failed"; return false; }
+    *out = p; return true;
+  };
+  for (int l = 0; l < nl; ++l) {
+    const MlpLayer& L = m.layers[l];
+    WideLayerDev& D = wm->L[l];
+    const bool last = l == nl - 1;
+    D.K = L.in; D.N = L.out;
+    D.Kp = wd_round_up(L.in, kWdChunkK);
+    D.NT = last ? 16 : (L.out % 256 == 0 ? 256 : (L.out % 128 == 0 ? 128 : 64));
+    D.Np = wd_round_up(L.out, D.NT);
+    D.has_elu = L.has_elu ? 1 : 0; D.alpha = L.elu_alpha;
+    if (l > 0 && D.Kp != wm->L[l - 1].Np) return -1;   // a hidden width that is not a multiple of 64
+    wm->max_kp = std::max(wm->max_kp, D.Kp);
+    std::vector<uint16_t> img;
+    for (int f = 0; f < 2; ++f) {
+      wd_pack_weights(L, D.NT, D.Np, D.Kp, f == 1, img);
+      void* p;
+      if (!upload(img.data(), img.size() * 2, &p)) return 4;
+      D.w[f] = static_cast<const uint16_t*>(p);
+    }
+    std::vector<float> bias(D.Np, 0.f);
+    for (int n = 0; n < L.out; ++n) bias[n] = L.bias[n];
+    void* pb;
+    if (!upload(bias.data(), bias.size() * 4, &pb)) return 4;
+    D.bias = static_cast<const float*>(pb);
+  }
+  return 0;
+}
+
+template <int NT, bool kFp16>
+inline cudaError_t wd_launch_gemm(const WideGemmArgs& a, int sm_count, cudaStream_t st) {
+  const size_t smem = (size_t)kWdStages * (kWdATileBytes + NT * kWdChunkK * 2) + 256;
+  cudaError_t e = cudaFuncSetAttribute(wide_gemm_kernel<NT, kFp16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const long long jobs = (long long)a.m_tiles * a.n_tiles;
+  const int grid = (int)std::min<long long>(jobs, sm_count);
+  wide_gemm_kernel<NT, kFp16><<<grid, kWdThreads, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+inline void wide_release(WideModel* wm) {
+  for (int s = 0; s < WideModel::kSets; ++s) {
+    for (int i = 0; i < 2; ++i) { if (wm->act[s][i]) cudaFree(wm->act[s][i]); wm->act[s][i] = nullptr; }
+    wm->act_rows[s] = 0;
+  }
+}
+
+constexpr long long kWdChunkRows = 16384;   // rows per pass: the widest activation (16384 x 1024 x 2 B = 32 MB) stays in L2
+
+inline int wide_launch(const WideModel& wm, const float* d_obs, const int32_t* d_button0, float* d_act, double* d_qdes, long long B,
+                       bool fp16, uint32_t flags, const CtrlConst& cc, int sm_count, cudaStream_t st, int* launches, std::string& err, int set = 0) {
+  if (set < 0 || set >= WideModel::kSets) { err = "wide_launch: bad stream set"; return 2; }
+  uint16_t** act = wm.act[set];
+  const long long chunk = std::min<long long>(B, kWdChunkRows);
+  const long long chunk_tiles = (chunk + kWdTileM - 1) / kWdTileM;
+  if (wm.act_rows[set] < chunk_tiles * kWdTileM) {
+    for (int i = 0; i < 2; ++i) { if (act[i]) cudaFree(act[i]); act[i] = nullptr; }
+    const size_t bytes = (size_t)chunk_tiles * kWdTileM * wm.max_kp * 2;
+    if (cudaMalloc((void**)&act[0], bytes) != cudaSuccess || cudaMalloc((void**)&act[1], bytes) != cudaSuccess) {
+      err = "wide_launch: cudaMalloc of the activation buffers failed"; return 4;
+    }
+    wm.act_rows[set] = chunk_tiles * kWdTileM;
+  }
+  for (long long r0 = 0; r0 < B; r0 += chunk) {
+    const long long rows = std::min(chunk, B - r0);
+    const int m_tiles = (int)((rows + kWdTileM - 1) / kWdTileM);
+    const WideLayerDev& L0 = wm.L[0];
+    {
+      const long long groups = (long long)m_tiles * kWdTileM * (L0.Kp / 8);
+      const int blocks = (int)std::min<long long>((groups + 255) / 256, (long long)sm_count * 8);
+      if (fp16) obs_to_blocked_kernel<true><<<blocks, 256, 0, st>>>(d_obs + r0 * wm.in_dim, act[0], rows, wm.in_dim, L0.Kp, m_tiles);
+      else obs_to_blocked_kernel<false><<<blocks, 256, 0, st>>>(d_obs + r0 * wm.in_dim, act[0], rows, wm.in_dim, L0.Kp, m_tiles);
+      ++*launches;
+    }
+    int cur = 0;
+    for (int l = 0; l < wm.n_layers; ++l) {
+      const WideLayerDev& L = wm.L[l];
+      const bool last = l == wm.n_layers - 1;
+      WideGemmArgs a{};
+      a.a = act[cur]; a.w = L.w[fp16 ? 1 : 0]; a.bias = L.bias;
+      a.out_blocked = last ? nullptr : act[cur ^ 1];
+      a.out_rows = last ? d_act + r0 * wm.out_dim : nullptr;
+      a.button0 = d_button0 ? d_button0 + r0 : nullptr;
+      a.qdes = d_qdes ? d_qdes + r0 * kDof : nullptr;
+      a.M = rows; a.m_tiles = m_tiles; a.n_tiles = L.Np / L.NT; a.k_chunks = L.Kp / kWdChunkK;
+      a.N = L.N; a.out_dim = wm.out_dim; a.has_elu = L.has_elu; a.alpha = L.alpha;
+      a.flags = last ? flags : 0u; a.action_limit = cc.action_limit; a.action_scale = cc.action_scale;
+      for (int i = 0; i < kDof; ++i) a.q0[i] = cc.q0[i];
+      cudaError_t e;
+      if (L.NT == 256) e = fp16 ? wd_launch_gemm<256, true>(a, sm_count, st) : wd_launch_gemm<256, false>(a, sm_count, st);
+      else if (L.NT == 128) e = fp16 ? wd_launch_gemm<128, true>(a, sm_count, st) : wd_launch_gemm<128, false>(a, sm_count, st);
+      else if (L.NT == 64) e = fp16 ? wd_launch_gemm<64, true>(a, sm_count, st) : wd_launch_gemm<64, false>(a, sm_count, st);
+      else e = fp16 ? wd_launch_gemm<16, true>(a, sm_count, st) : wd_launch_gemm<16, false>(a, sm_count, st);
+      if (e != cudaSuccess) { err = std::string("wide_launch: ") + cudaGetErrorString(e); return 4; }
+      ++*launches;
+      cur ^= 1;
+    }
+  }
+  return 0;
+}
+
 }  // namespace go2p
