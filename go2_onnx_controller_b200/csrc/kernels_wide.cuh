@@ -32,8 +32,9 @@ namespace go2p {
 constexpr int kWdTileM = 128;
 constexpr int kWdChunkK = 64;                       // K columns per pipeline stage (4 MMA K steps)
 constexpr int kWdATileBytes = kWdTileM * kWdChunkK * 2;   // 16 KB
-constexpr int kWdStages = 3;
-constexpr int kWdThreads = 6 * 32;                  // producer, MMA issuer, 4 epilogue warps
+constexpr int kWdStages = 4;                        // 4 x 48 KB (N tile 256) = 192 KB of operands in flight per SM
+constexpr int kWdEpiWarps = 8;                      // two per TMEM lane quarter, each takes half of the tile's columns
+constexpr int kWdThreads = (2 + kWdEpiWarps) * 32;  // producer, MMA issuer, epilogue warps
 
 // byte offset of element (r, c) inside a [rows x 64] blocked tile (rows multiple of 8)
 __host__ __device__ inline uint32_t wd_tile_offset(int r, int c) {
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemm
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < kWdStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
-      for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], 4); }
+      for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], kWdEpiWarps); }
       ptx::fence_mbar_init();
     }
     __syncwarp();
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemm
   } else {
     // ================= epilogue warps (lane quarter = warp % 4) =================
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;                // which half of the N tile's columns this warp converts
     const uint32_t lane_addr = ((uint32_t)(quarter * 32)) << 16;
     const int r = quarter * 32 + lane;               // row inside the tile
     uint32_t tile_i = 0;
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemm
         const int kcn_per_tile = NT / kWdChunkK;       // 64-column chunks of the next layer covered by this N tile
         const long long next_chunks = (long long)a.n_tiles * kcn_per_tile;
 #pragma unroll 1
-        for (int c0 = 0; c0 < NT; c0 += 32) {
+        for (int c0 = half * (NT / 2); c0 < (half + 1) * (NT / 2); c0 += 32) {
           uint32_t v[32];
           ptx::tmem_ld_x32(acc_t + (uint32_t)c0, v);
           ptx::tc_wait_ld();
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemm
         uint32_t v[16];
         ptx::tmem_ld_x16(acc_t, v);
         ptx::tc_wait_ld();
-        if (row < a.M) {
+        if (row < a.M && half == 0) {
           const int b0 = ((a.flags & 1u) && a.button0) ? a.button0[row] : 0;
           float* dst = a.out_rows + row * a.out_dim;
 #pragma unroll
@@ -332,7 +334,9 @@ inline void wide_release(WideModel* wm) {
   }
 }
 
-constexpr long long kWdChunkRows = 16384;   // rows per pass: the widest activation (16384 x 1024 x 2 B = 32 MB) stays in L2
+// rows per pass: 148 row tiles, so every layer's job count is a whole number of waves over the 148 SMs, and the widest
+// activation (18944 x 1024 x 2 B = 39 MB) still stays in the 126 MB L2 together with the next layer's output
+constexpr long long kWdChunkRows = 148 * kWdTileM;
 
 inline int wide_launch(const WideModel& wm, const float* d_obs, const int32_t* d_button0, float* d_act, double* d_qdes, long long B,
                        bool fp16, uint32_t flags, const CtrlConst& cc, int sm_count, cudaStream_t st, int* launches, std::string& err, int set = 0) {

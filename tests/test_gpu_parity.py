@@ -456,23 +456,24 @@ def test_wide_policy_fp32_path(torch_cuda, wide_model_path):
 @pytest.mark.parametrize("prec", [capi.PREC_FP16, capi.PREC_BF16])
 def test_wide_policy_tensor_core_path(torch_cuda, wide_model_path, prec):
     """configs[4] on the per-layer tcgen05 GEMM kernels (kernels_wide.cuh): ragged batches, a batch larger than one
-    L2-resident pass (16384 rows), the fused A9/A11 epilogue, and the host-buffer pipeline (concurrent streams)."""
+    L2-resident pass (148 row tiles = 18944 rows), the fused A9/A11 epilogue, and the host-buffer pipeline (concurrent streams)."""
     cm = coracle.CModel(wide_model_path)
     p = PolicyBatch(wide_model_path, history=5)
     tol = 2e-2 if prec == capi.PREC_FP16 else 1.2e-1
     try:
         assert p.info.tensor_core_path == 1
-        for B in (1, 129, 3001, 16384 + 16384 + 77):
+        CH = 148 * 128
+        for B in (1, 129, 3001, 2 * CH + 77):
             X = oracle.make_obs_d1(B, 245, seed=B)
             ref = cm.forward_f64(X, 8)
             y, _ = run_batch(torch_cuda, p, X, prec)
             err = np.abs(y - ref).max()
             print(f"wide TC prec={prec} B={B}: max abs err {err:.3e} (|ref| max {np.abs(ref).max():.2f})")
             assert err <= tol, err
-            assert p.last_launches() == 5 * ((B + 16383) // 16384)
+            assert p.last_launches() == 5 * ((B + CH - 1) // CH)
         # rows do not depend on the batch they are in (same tile arithmetic everywhere)
-        y1, _ = run_batch(torch_cuda, p, X[16384:16384 + 300], prec)
-        assert np.array_equal(bits(y1), bits(y[16384:16384 + 300]))
+        y1, _ = run_batch(torch_cuda, p, X[CH - 100:CH + 200], prec)
+        assert np.array_equal(bits(y1), bits(y[CH - 100:CH + 200]))
         # A9 / A11 epilogue bit-exact given the kernel's own raw action
         b0 = (np.arange(B) % 3 == 0).astype(np.int32)
         pub, qd = run_batch(torch_cuda, p, X * 50.0, prec, button0=b0, flags=capi.F_CLAMP_MASK | capi.F_QDES)
