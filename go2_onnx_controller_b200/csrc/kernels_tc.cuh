@@ -32,7 +32,10 @@
 #include "ptx_sm100.cuh"
 
 #ifndef GO2P_TC_POLY_PAIRS
-#define GO2P_TC_POLY_PAIRS 2
+#define GO2P_TC_POLY_PAIRS 1
+#endif
+#ifndef GO2P_TC_HALF_ELU
+#define GO2P_TC_HALF_ELU 1
 #endif
 
 namespace go2p {
@@ -126,6 +129,12 @@ __device__ __forceinline__ void elu_pack16(const uint32_t (&v)[16], bool has_elu
     const uint32_t zp = kFp16 ? ptx::pack_f16_sat(z0, z1) : ptx::pack_bf16(z0, z1);
     if (has_elu) {
       const bool poly = kFp16 && j >= 8 - kTcPolyPairs;   // bf16 keeps the MUFU everywhere (its budget has no slack)
+      if (GO2P_TC_HALF_ELU && kFp16 && !poly) {
+        // packed pair all the way: 2^z on the fp16 pair, c*e - c as one HFMA2 (6 instead of 8 instructions per pair)
+        const uint32_t c2 = ptx::pack_f16_sat(c, c), nc2 = ptx::pack_f16_sat(nc, nc);
+        p[j] = ptx::select_neg_f16x2(zp, ptx::fma_f16x2(ptx::ex2_f16x2(zp), c2, nc2));
+        continue;
+      }
       const float f0 = fmaf(poly ? ptx::ex2_poly(z0) : ptx::ex2_approx(z0), c, nc);
       const float f1 = fmaf(poly ? ptx::ex2_poly(z1) : ptx::ex2_approx(z1), c, nc);
       const uint32_t fp = kFp16 ? ptx::pack_f16_sat(f0, f1) : ptx::pack_bf16(f0, f1);
@@ -307,23 +316,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const TcArgs a) {
           }
           __syncwarp();
         } else {
+          // all four blocks, then the nine K steps back to back in the fixed order (block 0, bias, blocks 1..3).  The
+          // 16 pool warps finish a job within ~300 cycles of each other, so issuing block by block gained nothing and
+          // cost ~120 cycles of control-warp latency per MMA (wait + fence + elect per block) against ~55 when the
+          // MMAs are issued in one go -- enough to make the pool wait for the accumulator at every job.
+          for (int q = 0; q < kTcBlocks; ++q) ptx::mbar_wait(&blk[q], par);
+          ptx::tc_fence_after();
+          if (ptx::elect_one_sync()) {
+            TC_TRACE(0x200u | (uint32_t)(l << 4) | (uint32_t)s);
 #pragma unroll
-          for (int q = 0; q < kTcBlocks; ++q) {
-            const int cb = q;
-            ptx::mbar_wait(&blk[cb], par);
-            ptx::tc_fence_after();
-            if (ptx::elect_one_sync()) {
-              if (q == 0) TC_TRACE(0x200u | (uint32_t)(l << 4) | (uint32_t)s);
+            for (int cb = 0; cb < kTcBlocks; ++cb) {
               ptx::mma_f16_ts(dst, src + (uint32_t)(32 * cb), bdesc0 + (uint64_t)(2 * cb * 16), idesc, cb == 0 ? 0u : 1u);
               ptx::mma_f16_ts(dst, src + (uint32_t)(32 * cb + 8), bdesc0 + (uint64_t)((2 * cb + 1) * 16), idesc, 1u);
               if (cb == 0) ptx::mma_f16_ts(dst, src + 16u, bdesc0 + (uint64_t)(8 * 16), idesc, 1u);   // bias K step
-              if (q == kTcBlocks - 1) {
-                ptx::mma_commit(&acc_full[s]);
-                TC_TRACE(0x300u | (uint32_t)(l << 4) | (uint32_t)s);
-              }
             }
-            __syncwarp();
+            ptx::mma_commit(&acc_full[s]);
+            TC_TRACE(0x300u | (uint32_t)(l << 4) | (uint32_t)s);
           }
+          __syncwarp();
         }
         par ^= 1u;
         w_off += (uint32_t)(kp * nl * 2);
@@ -410,15 +420,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const TcArgs a) {
           ptx::tmem_ld_x16(d_t, cur);
           ptx::tmem_ld_x16(d_t + 16u, nxt);
           ptx::tc_wait_ld();
+          TC_TRACE(0xF00u | (1u << 4) | (uint32_t)s);
           elu_pack16<kFp16>(cur, he, c, pk);
+          TC_TRACE(0xF00u | (2u << 4) | (uint32_t)s);
           ptx::tmem_st_x8(d_t, pk);
           elu_pack16<kFp16>(nxt, he, c, pk);
+          TC_TRACE(0xF00u | (3u << 4) | (uint32_t)s);
           ptx::tmem_st_x8(d_t + 8u, pk);
           if (cb == 0) {   // constant-one columns (K = 128,129; zeros up to 143) in the dead half of block 0
             const uint32_t ones[8] = {one2, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
             ptx::tmem_st_x8(d_t + 16u, ones);
           }
           ptx::tc_wait_st();
+          TC_TRACE(0xF00u | (4u << 4) | (uint32_t)s);
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&a_blk[s * kTcBlocks + cb]);

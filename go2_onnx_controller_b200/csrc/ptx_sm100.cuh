@@ -203,6 +203,17 @@ __device__ __forceinline__ uint32_t select_neg_bf16x2(uint32_t z, uint32_t neg) 
   asm("set.lt.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(z), "r"(0u));
   return (neg & m) | (z & ~m);
 }
+// packed fp16 pair: 2^x (two MUFU.EX2.F16 operations) and a*b+c (one HFMA2)
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
+  uint32_t r;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+}
+__device__ __forceinline__ uint32_t fma_f16x2(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
 // 2^x for x <= 0 on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + r via the 1.5*2^23 trick,
 // degree-3 minimax polynomial for 2^r on [-0.5, 0.5] (max relative error 7.5e-5, below half an fp16 ulp), exponent
 // patched in with an integer add.  Inputs below -24 are clamped (2^-24 is far below the resolution of c*(2^x - 1));
