@@ -274,6 +274,34 @@ def main():
     if rank == 0:
         line["parity_max_abs_err_vs_oracle"] = parity_err
         line["batch4096"] = small
+    if rank == 0 and world == 1:
+        # the whole publish() for `rows` robots (raw state -> history -> policy -> clamp/mask -> q_des),
+        # two launches per step, per-robot state resident in HBM (go2p_step_batch)
+        from oracle import oracle as _o
+        import __graft_entry__ as ge
+        import ctypes as C
+        base = [ge.coracle_to_capi(r, capi) for r in _o.make_raw_states(4096, seed=3)]
+        arr = (capi.RawState * 4096)(*base)
+        raw_np = np.frombuffer(bytes(arr), np.uint8).reshape(4096, C.sizeof(capi.RawState))
+        d_raw = torch.from_numpy(np.tile(raw_np, (rows // 4096 + 1, 1))[:rows].copy()).to("cuda")
+        s_obs = torch.zeros((rows, 98), device="cuda"); s_vel = torch.zeros((rows, 3), device="cuda")
+        s_act = torch.zeros((rows, 12), device="cuda"); s_q = torch.zeros((rows, 12), device="cuda", dtype=torch.float64)
+        def ctl_step():
+            pb.step_device(d_raw.data_ptr(), s_vel.data_ptr(), s_obs.data_ptr(), s_act.data_ptr(), s_q.data_ptr(), rows, prec, stream)
+        for _ in range(3):
+            ctl_step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_ctl = max(3, min(args.steps, 10))
+        e0.record()
+        for _ in range(n_ctl):
+            ctl_step()
+        e1.record(); torch.cuda.synchronize()
+        ctl_ms = e0.elapsed_time(e1) / n_ctl
+        line["batched_step"] = {"robots": rows, "ms_per_step": ctl_ms, "robot_steps_per_sec": rows / (ctl_ms * 1e-3),
+                                "launches_per_step": pb.last_launches(),
+                                "note": "go2p_step_batch: A1-A6 assembly kernel + fused A7/A9/A11 kernel, state in HBM"}
+        del d_raw, s_obs, s_vel, s_act, s_q
     if rank == 0 and world == 1 and not args.no_b1:
         # BASELINE.json configs[1]: batch-1 closed loop, fused pre/post, resident kernel
         from oracle import oracle as _o

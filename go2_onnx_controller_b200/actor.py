@@ -193,5 +193,12 @@ class PolicyBatch:
     def assemble_device(self, d_raw: int, d_prev_action: int | None, d_vel_cmd: int, d_obs: int, B: int, stream: int = 0):
         capi.check(self._hd.lib.go2p_assemble_batch(self._hd.h, d_raw, d_prev_action, d_vel_cmd, d_obs, B, stream or None))
 
+    def step_device(self, d_raw: int, d_vel_cmd: int, d_obs: int, d_action: int, d_qdes: int, B: int,
+                    precision: int = capi.PREC_FP32, stream: int = 0) -> None:
+        """Batched publish() (reference: controller.cpp:173-251 per robot): raw states -> observation history ->
+        policy -> clamp/mask -> q_des, all on device buffers; d_action is the previous published action on entry."""
+        capi.check(self._hd.lib.go2p_step_batch(self._hd.h, d_raw, d_vel_cmd, d_obs, d_action, d_qdes, B, precision,
+                                                stream or None))
+
     def close(self) -> None:
         self._hd.close()

@@ -84,6 +84,8 @@ SIGNATURES = {
                                        C.c_uint32, C.c_void_p]),
     "go2p_infer_batch_host": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     "go2p_assemble_batch": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "go2p_step_batch": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                  C.c_void_p]),
     "go2p_last_launch_count": (C.c_int, [_H]),
     "go2p_dev_alloc": (C.c_int, [_H, C.c_size_t, C.POINTER(C.c_void_p)]),
     "go2p_dev_free": (C.c_int, [_H, C.c_void_p]),

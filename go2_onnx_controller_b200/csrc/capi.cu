@@ -78,6 +78,8 @@ struct go2p_handle {
   int scratch_sel = 0;
   // batch-1
   B1State* d_state = nullptr;
+  int32_t* d_step_button = nullptr;   // go2p_step_batch: dead-man buttons extracted by the assembly kernel
+  int64_t step_button_rows = 0;
   MailWord* inbox = nullptr;    // host-mapped
   MailWord* outbox = nullptr;   // host-mapped
   int n_in_slots = 0;
@@ -582,6 +584,7 @@ int go2p_destroy(go2p_handle* h) {
   for (auto& sc : h->scratch_sets)
     for (int i = 0; i < 2; ++i) if (sc.buf[i]) cudaFree(sc.buf[i]);
   if (h->d_state) cudaFree(h->d_state);
+  if (h->d_step_button) cudaFree(h->d_step_button);
   if (h->inbox) cudaFreeHost(h->inbox);
   if (h->outbox) cudaFreeHost(h->outbox);
   delete h;
@@ -877,14 +880,36 @@ int go2p_assemble_batch(go2p_handle* h, const go2p_raw_state* d_raw, const float
   if (!h || !d_raw || !d_vel_cmd || !d_obs) return fail(GO2P_ERR_INVALID, "go2p_assemble_batch: null argument");
   if (B <= 0) return B == 0 ? GO2P_OK : fail(GO2P_ERR_INVALID, "negative batch");
   DeviceGuard g(h->device);
-  const int n_obs = kFrame * h->cc.H;
-  const int threads = round_up(n_obs, 32);
-  const unsigned grid = (unsigned)std::min<int64_t>(B, (int64_t)h->sm_count * 16);
-  assemble_batch_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const RawStateDev*>(d_raw), d_prev_action, d_vel_cmd, d_obs, B, h->cc);
+  launch_assemble_batch(reinterpret_cast<const RawStateDev*>(d_raw), d_prev_action, d_vel_cmd, d_obs, B, h->cc, nullptr,
+                        h->sm_count, static_cast<cudaStream_t>(stream));
   h->last_launches = 1;
   CU_TRY(cudaGetLastError());
   return GO2P_OK;
+}
+
+int go2p_step_batch(go2p_handle* h, const go2p_raw_state* d_raw, float* d_vel_cmd, float* d_obs, float* d_action,
+                    double* d_qdes, int64_t B, int precision, void* stream) {
+  if (!h || !d_raw || !d_vel_cmd || !d_obs || !d_action || !d_qdes)
+    return fail(GO2P_ERR_INVALID, "go2p_step_batch: null argument");
+  if (B <= 0) return B == 0 ? GO2P_OK : fail(GO2P_ERR_INVALID, "negative batch");
+  if (h->dm.in_dim != kFrame * h->cc.H || h->dm.out_dim != kDof)
+    return fail(GO2P_ERR_INVALID, "go2p_step_batch: the policy is not a 49*H -> 12 controller policy");
+  DeviceGuard g(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (h->step_button_rows < B) {
+    if (h->d_step_button) { CU_TRY(cudaStreamSynchronize(st)); CU_TRY(cudaFree(h->d_step_button)); h->d_step_button = nullptr; }
+    CU_TRY(cudaMalloc((void**)&h->d_step_button, (size_t)B * sizeof(int32_t)));
+    h->step_button_rows = B;
+  }
+  // A1-A6: d_action still holds the previous published action here
+  launch_assemble_batch(reinterpret_cast<const RawStateDev*>(d_raw), d_action, d_vel_cmd, d_obs, B, h->cc, h->d_step_button,
+                        h->sm_count, st);
+  CU_TRY(cudaGetLastError());
+  // A7 + A9 + A11
+  const int rc = go2p_infer_batch_ex(h, d_obs, h->d_step_button, d_action, d_qdes, B, precision,
+                                     GO2P_F_CLAMP_MASK | GO2P_F_QDES, stream);
+  if (rc == GO2P_OK) h->last_launches += 1;
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------- helpers

@@ -8,6 +8,7 @@
 //                           (clamp + dead-man mask, q_des; reference: controller.cpp:217-223,244)
 //   assemble_batch_kernel : A1-A6 for B robots (reference: controller.cpp:173-212)
 #pragma once
+#include <algorithm>
 #include "kernels_b1.cuh"
 #include "policy_dev.cuh"
 
@@ -169,42 +170,118 @@ struct RawStateDev {
 };
 static_assert(sizeof(RawStateDev) == 4 * 35 + 8 + 8, "must match go2p_raw_state");
 
-__global__ void assemble_batch_kernel(const RawStateDev* __restrict__ raw, const float* __restrict__ prev_action,
-                                      float* __restrict__ vel_cmd, float* __restrict__ obs, long long B, CtrlConst cc) {
+// button0_out (optional): the dead-man button of every robot as int32 [B], the form the batched epilogue reads.
+// One WARP per robot row.  Lane i owns elements i, i+32, ... of the 49*H-float row; it reads all of them (old
+// frames from the row itself, the newest frame from the raw state) into registers and only then writes, so the
+// in-place shift needs no block barrier and rows move as contiguous segments.  The 156-byte raw state is loaded
+// once per row as 39 coalesced words and handed out by warp shuffles; the gravity projection and the joystick
+// command are evaluated by every lane (no divergence), with the same operations as the batch-1 kernel
+// (kernels_b1.cuh: gravity_component, vel_cmd_component), so results are bit-identical to it.
+constexpr int kAsmWarps = 8;
+
+template <int kPerLane>
+__global__ void __launch_bounds__(kAsmWarps * 32)
+assemble_batch_kernel(const RawStateDev* __restrict__ raw, const float* __restrict__ prev_action,
+                      float* __restrict__ vel_cmd, float* __restrict__ obs, long long B, CtrlConst cc,
+                      int32_t* __restrict__ button0_out) {
+  constexpr unsigned kFull = 0xffffffffu;
   const int H = cc.H, n_obs = kFrame * H;
-  // a CTA handles rows in groups: blockDim.x threads >= n_obs; one row per CTA iteration
-  for (long long row = blockIdx.x; row < B; row += gridDim.x) {
-    const int tid = threadIdx.x;
-    const RawStateDev* r = raw + row;
-    float* o = obs + row * n_obs;
-    float v = 0.f; int t = 0, c = 0; bool newest = false;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * kAsmWarps + (threadIdx.x >> 5);
+  const long long n_warps = (long long)gridDim.x * kAsmWarps;
+  // element classification is row-independent: hoisted out of the row loop.
+  // meta = -1: no element; bit 8: old frame, low byte = distance to the value to copy; else newest frame:
+  // term in bits 4..6, component in bits 0..3
+  int meta[kPerLane];
+  double q0e[kPerLane];                                    // default pose of the joint behind a (q - q0) element
+#pragma unroll
+  for (int e = 0; e < kPerLane; ++e) {
+    const int tid = e * 32 + lane;
+    meta[e] = -1;
+    q0e[e] = 0.0;
     if (tid < n_obs) {
-      int off, wdt;
+      int t, off, wdt;
       if (tid < 9 * H) { t = tid / (3 * H); off = t * 3 * H; wdt = 3; }
       else if (tid < 45 * H) { t = 3 + (tid - 9 * H) / (12 * H); off = 9 * H + (t - 3) * 12 * H; wdt = 12; }
       else { t = 6; off = 45 * H; wdt = 4; }
-      const int local = tid - off; const int f = local / wdt; c = local - f * wdt;
-      newest = (f == H - 1);
-      if (!newest) v = o[tid + wdt];
-      else {
-        switch (t) {
-          case 0: v = gravity_component(r->quat, c); break;
-          case 1: v = r->gyro[c]; break;
-          case 2: v = r->joy_valid ? vel_cmd_component(r->axes, c) : vel_cmd[row * 3 + c]; break;
-          case 3: v = __double2float_rn(__dsub_rn((double)r->q[c], cc.q0[c])); break;
-          case 4: v = r->dq[c]; break;
-          case 5: v = prev_action ? prev_action[row * kDof + c] : 0.f; break;
-          default: v = ((int)r->foot_force[c ^ 1] >= cc.foot_threshold) ? 1.0f : 0.0f; break;
-        }
+      const int local = tid - off; const int f = local / wdt; const int c = local - f * wdt;
+      meta[e] = (f != H - 1) ? (0x100 | wdt) : ((t << 4) | c);
+      if (f == H - 1 && t == 3) q0e[e] = cc.q0[c];
+    }
+  }
+  // software pipeline over rows: the raw words and the old-frame values of the NEXT row are requested before the
+  // current row is evaluated, so every warp always has one row's worth of DRAM latency in flight
+  uint32_t nw0 = 0u, nw1 = 0u;
+  float nv[kPerLane];
+  auto request = [&](long long row) {
+    const uint32_t* rw = reinterpret_cast<const uint32_t*>(raw + row);
+    const float* o = obs + row * n_obs;
+    nw0 = rw[lane];                                        // words 0..31: quat, gyro, q, dq, axes[0]
+    nw1 = lane < 7 ? rw[32 + lane] : 0u;                   // words 32..38: axes[1..3], foot_force (2), joy_valid, button0
+#pragma unroll
+    for (int e = 0; e < kPerLane; ++e)
+      nv[e] = (meta[e] >= 0 && (meta[e] & 0x100)) ? o[e * 32 + lane + (meta[e] & 0xff)] : 0.f;
+  };
+  if (warp0 < B) request(warp0);
+  for (long long row = warp0; row < B; row += n_warps) {
+    float* o = obs + row * n_obs;
+    const uint32_t w0 = nw0, w1 = nw1;
+    float v[kPerLane];
+#pragma unroll
+    for (int e = 0; e < kPerLane; ++e) v[e] = nv[e];
+    if (row + n_warps < B) request(row + n_warps);
+    float quat[4], axes[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) quat[i] = __uint_as_float(__shfl_sync(kFull, w0, i));
+    axes[0] = __uint_as_float(__shfl_sync(kFull, w0, 31));
+#pragma unroll
+    for (int i = 1; i < 4; ++i) axes[i] = __uint_as_float(__shfl_sync(kFull, w1, i - 1));
+    const uint32_t ff01 = __shfl_sync(kFull, w1, 3), ff23 = __shfl_sync(kFull, w1, 4);
+    const int joy_valid = (int)__shfl_sync(kFull, w1, 5);
+    const float g0 = gravity_component(quat, 0), g1 = gravity_component(quat, 1), g2 = gravity_component(quat, 2);
+    float c0, c1, c2;
+    if (joy_valid) { c0 = vel_cmd_component(axes, 0); c1 = vel_cmd_component(axes, 1); c2 = vel_cmd_component(axes, 2); }
+    else { c0 = vel_cmd[row * 3 + 0]; c1 = vel_cmd[row * 3 + 1]; c2 = vel_cmd[row * 3 + 2]; }   // warp-uniform branch
+#pragma unroll
+    for (int e = 0; e < kPerLane; ++e) {
+      const int mt = meta[e];
+      const bool fresh = mt >= 0 && !(mt & 0x100);
+      const int t = (mt >> 4) & 7, c = mt & 15;
+      // raw word behind a copied term: gyro 4+c, q 7+c, dq 19+c (all within the first 32 words)
+      const int src = t == 1 ? 4 + c : (t == 3 ? 7 + c : 19 + c);
+      const float x = __uint_as_float(__shfl_sync(kFull, w0, fresh ? src : 0));
+      if (fresh) {
+        float r;
+        if (t == 0) r = c == 0 ? g0 : (c == 1 ? g1 : g2);
+        else if (t == 2) r = c == 0 ? c0 : (c == 1 ? c1 : c2);
+        else if (t == 3) r = __double2float_rn(__dsub_rn((double)x, q0e[e]));
+        else if (t == 5) r = prev_action ? prev_action[row * kDof + c] : 0.f;
+        else if (t == 6) {
+          const int p = c ^ 1;                                  // [1,0,3,2]
+          const uint32_t wpair = (p >> 1) ? ff23 : ff01;
+          const int f = (int)(int16_t)(uint16_t)(wpair >> (16 * (p & 1)));
+          r = (f >= cc.foot_threshold) ? 1.0f : 0.0f;
+        } else r = x;                                           // gyro, dq
+        v[e] = r;
       }
     }
-    block_sync();
-    if (tid < n_obs) {
-      o[tid] = v;
-      if (newest && t == 2) vel_cmd[row * 3 + c] = v;
-    }
-    block_sync();
+    __syncwarp();      // every lane holds its old values before any lane overwrites them
+#pragma unroll
+    for (int e = 0; e < kPerLane; ++e)
+      if (meta[e] >= 0) o[e * 32 + lane] = v[e];
+    if (lane < 3 && joy_valid) vel_cmd[row * 3 + lane] = lane == 0 ? c0 : (lane == 1 ? c1 : c2);
+    if (lane == 6 && button0_out) button0_out[row] = (int32_t)w1;
   }
+}
+
+// n_obs = 49*H floats per row: 4 elements per lane serve H <= 2, 13 serve H <= 8
+inline void launch_assemble_batch(const RawStateDev* raw, const float* prev_action, float* vel_cmd, float* obs, long long B,
+                                  const CtrlConst& cc, int32_t* button0_out, int sm_count, cudaStream_t st) {
+  const unsigned grid = (unsigned)std::min<long long>((B + kAsmWarps - 1) / kAsmWarps, (long long)sm_count * 32);
+  if (kFrame * cc.H <= 128)
+    assemble_batch_kernel<4><<<grid, kAsmWarps * 32, 0, st>>>(raw, prev_action, vel_cmd, obs, B, cc, button0_out);
+  else
+    assemble_batch_kernel<(kFrame * kMaxHistory + 31) / 32><<<grid, kAsmWarps * 32, 0, st>>>(raw, prev_action, vel_cmd, obs, B, cc, button0_out);
 }
 
 }  // namespace go2p

@@ -479,6 +479,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const TcArgs a) {
         ptx::tc_fence_before();
         TC_TRACE(0x900u | (uint32_t)s);
       }
+      // With an even number of hidden layers the output accumulator shares its TMEM buffer with the next tile's
+      // layer-0 operand: the four warps of a lane quarter (the only ones touching these lanes) meet before any of them
+      // converts the next tile, so no conversion store can overtake a sibling's output read.  (Odd counts -- the Go2
+      // policy -- use the other buffer and skip this.)
+      if ((L & 1) == 0) {
+        __syncwarp();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
+      }
     }
   }
 

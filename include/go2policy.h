@@ -181,6 +181,13 @@ int go2p_infer_batch_host(go2p_handle* h, const float* h_obs, float* h_act, int6
  * d_obs [B,49*H] is read (old frames) and rewritten in place. */
 int go2p_assemble_batch(go2p_handle* h, const go2p_raw_state* d_raw, const float* d_prev_action,
                         float* d_vel_cmd, float* d_obs, int64_t B, void* stream);
+/* batched publish() for B robots (reference: controller.cpp:173-251 once per robot): A1-A6 -> A7 -> A9 -> A11 on
+ * device buffers, two launches (assembly, fused policy kernel).  Per-robot state lives in the caller's buffers:
+ * d_obs [B,49*H] history (in/out), d_vel_cmd [B,3] last joystick command (in/out), d_action [B,12] previous
+ * published action on entry, new published (clamped, masked) action on return; d_qdes [B,12] double out.
+ * kp/kd are per-robot functions of button0 alone (controller.cpp:246) and stay with the caller. */
+int go2p_step_batch(go2p_handle* h, const go2p_raw_state* d_raw, float* d_vel_cmd, float* d_obs,
+                    float* d_action, double* d_qdes, int64_t B, int precision, void* stream);
 /* number of kernels the previous batched call launched (for bench.py's gpu_launches) */
 int go2p_last_launch_count(const go2p_handle* h);
 

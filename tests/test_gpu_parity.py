@@ -378,6 +378,51 @@ def test_batched_observation_assembly_bit_exact(torch_cuda, pb, golden_loop):
         assert np.array_equal(bits(got[:, 6:]), bits(exp[:, 6:])), s
 
 
+@pytest.mark.parametrize("prec", [capi.PREC_FP32, capi.PREC_FP16])
+def test_batched_controller_step_closed_loop(torch_cuda, pb, policy, golden_loop, prec):
+    """go2p_step_batch = publish() for B robots in two launches (A1-A6, then A7+A9+A11), per-robot history on the
+    device, the published action fed back as the next step's previous action (reference: controller.cpp:173-251).
+    Every step is compared with the restated publish() re-synchronised to the device's own published action."""
+    torch = torch_cuda
+    g = golden_loop
+    B, steps = 80, 6
+    n_g = g["obs"].shape[0]
+    states = [oracle.ControllerState(H=2) for _ in range(B)]
+    d_obs = torch.zeros((B, 98), device="cuda", dtype=torch.float32)
+    d_vel = torch.zeros((B, 3), device="cuda", dtype=torch.float32)
+    d_act = torch.zeros((B, 12), device="cuda", dtype=torch.float32)
+    d_q = torch.zeros((B, 12), device="cuda", dtype=torch.float64)
+    tol = TOL_FP32 if prec == capi.PREC_FP32 else 1e-2
+    masked = 0
+    for s in range(steps):
+        raws = (capi.RawState * B)()
+        idx = [(7 * s * B + 3 * b) % n_g for b in range(B)]
+        for b in range(B):
+            raws[b] = raw_struct(g, idx[b])
+            if (b + s) % 9 == 0:
+                raws[b].button0 = 1          # dead-man pressed on some robots
+        d_raw = torch.from_numpy(np.frombuffer(bytes(raws), np.uint8).copy()).cuda()
+        pb.step_device(d_raw.data_ptr(), d_vel.data_ptr(), d_obs.data_ptr(), d_act.data_ptr(), d_q.data_ptr(), B, prec)
+        torch.cuda.synchronize()
+        assert pb.last_launches() == (5 if prec == capi.PREC_FP32 else 2)
+        obs, act, qd = d_obs.cpu().numpy(), d_act.cpu().numpy(), d_q.cpu().numpy()
+        for b in range(B):
+            raw = raw_py(g, idx[b])
+            raw.button0 = int(raws[b].button0)
+            so = oracle.controller_step(policy, states[b], raw, np.float64, act_fn=lambda o: oracle.forward(policy, obs[b], np.float64))
+            assert np.abs(bits(obs[b, :6]).astype(np.int64) - bits(so.obs[:6]).astype(np.int64)).max() <= 1, (s, b)
+            assert np.array_equal(bits(obs[b, 6:]), bits(so.obs[6:])), (s, b)
+            assert (np.abs(act[b] - so.action) / np.maximum(1, np.abs(so.action))).max() <= tol, (s, b)
+            if raw.button0:
+                masked += 1
+                assert not act[b].any()                                   # masked to (signed) zero
+            exp_q, _, _ = oracle.joint_targets(act[b], raw.button0)
+            assert np.array_equal(qd[b].view(np.uint64), exp_q.view(np.uint64)), (s, b)   # A11 bit-exact (double)
+            states[b].action = act[b].copy()           # closed loop on the device's own published action
+            states[b].hist[0][:] = obs[b, :6]          # keep the <= 1-ulp gravity difference from accumulating
+    assert masked > 20
+
+
 def test_resident_kernel_coexists_with_batched_kernels(torch_cuda, model_path, golden):
     """One handle: the batch-1 resident kernel keeps answering while batched launches share the device."""
     obs, act = np.zeros(98, np.float32), np.zeros(12, np.float32)
