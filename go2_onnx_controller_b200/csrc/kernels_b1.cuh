@@ -73,8 +73,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // gb = quaternion_.inverse() * (0,0,-1), Eigen semantics, fp32, no FMA contraction
-// (reference: controller.cpp:182-184).  Returns component c.
-__device__ __forceinline__ float gravity_component(const float* quat_wxyz, int c) {
+// (reference: controller.cpp:182-184).  gravity_all: the three components; gravity_component: component c.
+__device__ __forceinline__ void gravity_all(const float* quat_wxyz, float (&g)[3]) {
   const float w = quat_wxyz[0], x = quat_wxyz[1], y = quat_wxyz[2], z = quat_wxyz[3];
   const float n2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)), __fmul_rn(w, w));
   float cw = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f;
@@ -87,9 +87,14 @@ __device__ __forceinline__ float gravity_component(const float* quat_wxyz, int c
   const float b0 = __fsub_rn(__fmul_rn(u1, a2), __fmul_rn(u2, a1));
   const float b1 = __fsub_rn(__fmul_rn(u2, a0), __fmul_rn(u0, a2));
   const float b2 = __fsub_rn(__fmul_rn(u0, a1), __fmul_rn(u1, a0));
-  if (c == 0) return __fadd_rn(__fadd_rn(v0, __fmul_rn(cw, a0)), b0);
-  if (c == 1) return __fadd_rn(__fadd_rn(v1, __fmul_rn(cw, a1)), b1);
-  return __fadd_rn(__fadd_rn(v2, __fmul_rn(cw, a2)), b2);
+  g[0] = __fadd_rn(__fadd_rn(v0, __fmul_rn(cw, a0)), b0);
+  g[1] = __fadd_rn(__fadd_rn(v1, __fmul_rn(cw, a1)), b1);
+  g[2] = __fadd_rn(__fadd_rn(v2, __fmul_rn(cw, a2)), b2);
+}
+__device__ __forceinline__ float gravity_component(const float* quat_wxyz, int c) {
+  float g[3];
+  gravity_all(quat_wxyz, g);
+  return c == 0 ? g[0] : (c == 1 ? g[1] : g[2]);
 }
 
 // vel_cmd from joystick axes (reference: controller.cpp:176-178; double pow path, -0.0f at axes[0]==0)

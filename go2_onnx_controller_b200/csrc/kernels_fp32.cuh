@@ -171,113 +171,134 @@ struct RawStateDev {
 static_assert(sizeof(RawStateDev) == 4 * 35 + 8 + 8, "must match go2p_raw_state");
 
 // button0_out (optional): the dead-man button of every robot as int32 [B], the form the batched epilogue reads.
-// One WARP per robot row.  Lane i owns elements i, i+32, ... of the 49*H-float row; it reads all of them (old
-// frames from the row itself, the newest frame from the raw state) into registers and only then writes, so the
-// in-place shift needs no block barrier and rows move as contiguous segments.  The 156-byte raw state is loaded
-// once per row as 39 coalesced words and handed out by warp shuffles; the gravity projection and the joystick
-// command are evaluated by every lane (no divergence), with the same operations as the batch-1 kernel
-// (kernels_b1.cuh: gravity_component, vel_cmd_component), so results are bit-identical to it.
-constexpr int kAsmWarps = 8;
+// A warp takes 32 robots at a time:
+//   1. their raw states (32 x 156 B, contiguous) are copied to shared memory with coalesced loads;
+//   2. lane r evaluates the newest frame of robot r (49 values: gravity projection, gyro, command, q - q0, dq,
+//      previous action, contacts) -- one robot per lane, so the scalar work of a robot is not replicated over a warp --
+//      with the same device functions as the batch-1 kernel (kernels_b1.cuh), i.e. bit-identical results;
+//   3. the warp walks the 32 observation rows: every lane reads its elements of a row (old frames from the row itself,
+//      the newest frame from shared memory), then writes them back shifted -- coalesced 392-byte rows, no block
+//      barrier, several rows of loads in flight.
+constexpr int kAsmWarps = 4;
+constexpr int kAsmRawWords = 39;                        // sizeof(RawStateDev) / 4
+constexpr int kAsmRowsInFlight = 4;
 
 template <int kPerLane>
 __global__ void __launch_bounds__(kAsmWarps * 32)
 assemble_batch_kernel(const RawStateDev* __restrict__ raw, const float* __restrict__ prev_action,
                       float* __restrict__ vel_cmd, float* __restrict__ obs, long long B, CtrlConst cc,
                       int32_t* __restrict__ button0_out) {
-  constexpr unsigned kFull = 0xffffffffu;
+  __shared__ uint32_t s_raw[kAsmWarps][32 * kAsmRawWords];
+  __shared__ float s_new[kAsmWarps][32 * kFrame];
   const int H = cc.H, n_obs = kFrame * H;
-  const int lane = threadIdx.x & 31;
-  const long long warp0 = (long long)blockIdx.x * kAsmWarps + (threadIdx.x >> 5);
-  const long long n_warps = (long long)gridDim.x * kAsmWarps;
-  // element classification is row-independent: hoisted out of the row loop.
-  // meta = -1: no element; bit 8: old frame, low byte = distance to the value to copy; else newest frame:
-  // term in bits 4..6, component in bits 0..3
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t* my_raw = s_raw[wid];
+  float* my_new = s_new[wid];
+  // element classification is row-independent.  meta = -1: no element; bit 8 set: old frame, low byte = distance
+  // to the value to copy; else newest frame, low byte = index inside the 49-value frame
   int meta[kPerLane];
-  double q0e[kPerLane];                                    // default pose of the joint behind a (q - q0) element
 #pragma unroll
   for (int e = 0; e < kPerLane; ++e) {
     const int tid = e * 32 + lane;
     meta[e] = -1;
-    q0e[e] = 0.0;
     if (tid < n_obs) {
       int t, off, wdt;
       if (tid < 9 * H) { t = tid / (3 * H); off = t * 3 * H; wdt = 3; }
       else if (tid < 45 * H) { t = 3 + (tid - 9 * H) / (12 * H); off = 9 * H + (t - 3) * 12 * H; wdt = 12; }
       else { t = 6; off = 45 * H; wdt = 4; }
       const int local = tid - off; const int f = local / wdt; const int c = local - f * wdt;
-      meta[e] = (f != H - 1) ? (0x100 | wdt) : ((t << 4) | c);
-      if (f == H - 1 && t == 3) q0e[e] = cc.q0[c];
+      meta[e] = (f != H - 1) ? (0x100 | wdt) : (frame_offset(t) + c);
     }
   }
-  // software pipeline over rows: the raw words and the old-frame values of the NEXT row are requested before the
-  // current row is evaluated, so every warp always has one row's worth of DRAM latency in flight
-  uint32_t nw0 = 0u, nw1 = 0u;
-  float nv[kPerLane];
-  auto request = [&](long long row) {
-    const uint32_t* rw = reinterpret_cast<const uint32_t*>(raw + row);
-    const float* o = obs + row * n_obs;
-    nw0 = rw[lane];                                        // words 0..31: quat, gyro, q, dq, axes[0]
-    nw1 = lane < 7 ? rw[32 + lane] : 0u;                   // words 32..38: axes[1..3], foot_force (2), joy_valid, button0
+  const long long n_groups = (B + 31) / 32;
+  for (long long grp = (long long)blockIdx.x * kAsmWarps + wid; grp < n_groups; grp += (long long)gridDim.x * kAsmWarps) {
+    const long long row0 = grp * 32;
+    const int rows = (int)min(32LL, B - row0);
+    // 1. raw states of the group -> shared memory (contiguous words, coalesced)
+    const uint32_t* gr = reinterpret_cast<const uint32_t*>(raw + row0);
+    for (int i = lane; i < rows * kAsmRawWords; i += 32) my_raw[i] = gr[i];
+    __syncwarp();
+    // 2. newest frame of robot (row0 + lane)
+    if (lane < rows) {
+      const long long row = row0 + lane;
+      const uint32_t* rw = my_raw + lane * kAsmRawWords;          // stride 39 words: conflict-free
+      const float* rf = reinterpret_cast<const float*>(rw);
+      float* nf = my_new + lane * kFrame;                          // stride 49 words: conflict-free
+      float quat[4] = {rf[0], rf[1], rf[2], rf[3]};
+      float g[3];
+      gravity_all(quat, g);
+      nf[0] = g[0]; nf[1] = g[1]; nf[2] = g[2];
 #pragma unroll
-    for (int e = 0; e < kPerLane; ++e)
-      nv[e] = (meta[e] >= 0 && (meta[e] & 0x100)) ? o[e * 32 + lane + (meta[e] & 0xff)] : 0.f;
-  };
-  if (warp0 < B) request(warp0);
-  for (long long row = warp0; row < B; row += n_warps) {
-    float* o = obs + row * n_obs;
-    const uint32_t w0 = nw0, w1 = nw1;
-    float v[kPerLane];
+      for (int c = 0; c < 3; ++c) nf[3 + c] = rf[4 + c];
+      const int joy_valid = (int)rw[37];
+      float axes[4] = {rf[31], rf[32], rf[33], rf[34]};
+      float cmd[3];
+      if (joy_valid) {
 #pragma unroll
-    for (int e = 0; e < kPerLane; ++e) v[e] = nv[e];
-    if (row + n_warps < B) request(row + n_warps);
-    float quat[4], axes[4];
+        for (int c = 0; c < 3; ++c) { cmd[c] = vel_cmd_component(axes, c); vel_cmd[row * 3 + c] = cmd[c]; }
+      } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) quat[i] = __uint_as_float(__shfl_sync(kFull, w0, i));
-    axes[0] = __uint_as_float(__shfl_sync(kFull, w0, 31));
+        for (int c = 0; c < 3; ++c) cmd[c] = vel_cmd[row * 3 + c];
+      }
 #pragma unroll
-    for (int i = 1; i < 4; ++i) axes[i] = __uint_as_float(__shfl_sync(kFull, w1, i - 1));
-    const uint32_t ff01 = __shfl_sync(kFull, w1, 3), ff23 = __shfl_sync(kFull, w1, 4);
-    const int joy_valid = (int)__shfl_sync(kFull, w1, 5);
-    const float g0 = gravity_component(quat, 0), g1 = gravity_component(quat, 1), g2 = gravity_component(quat, 2);
-    float c0, c1, c2;
-    if (joy_valid) { c0 = vel_cmd_component(axes, 0); c1 = vel_cmd_component(axes, 1); c2 = vel_cmd_component(axes, 2); }
-    else { c0 = vel_cmd[row * 3 + 0]; c1 = vel_cmd[row * 3 + 1]; c2 = vel_cmd[row * 3 + 2]; }   // warp-uniform branch
+      for (int c = 0; c < 3; ++c) nf[6 + c] = cmd[c];
 #pragma unroll
-    for (int e = 0; e < kPerLane; ++e) {
-      const int mt = meta[e];
-      const bool fresh = mt >= 0 && !(mt & 0x100);
-      const int t = (mt >> 4) & 7, c = mt & 15;
-      // raw word behind a copied term: gyro 4+c, q 7+c, dq 19+c (all within the first 32 words)
-      const int src = t == 1 ? 4 + c : (t == 3 ? 7 + c : 19 + c);
-      const float x = __uint_as_float(__shfl_sync(kFull, w0, fresh ? src : 0));
-      if (fresh) {
-        float r;
-        if (t == 0) r = c == 0 ? g0 : (c == 1 ? g1 : g2);
-        else if (t == 2) r = c == 0 ? c0 : (c == 1 ? c1 : c2);
-        else if (t == 3) r = __double2float_rn(__dsub_rn((double)x, q0e[e]));
-        else if (t == 5) r = prev_action ? prev_action[row * kDof + c] : 0.f;
-        else if (t == 6) {
-          const int p = c ^ 1;                                  // [1,0,3,2]
-          const uint32_t wpair = (p >> 1) ? ff23 : ff01;
-          const int f = (int)(int16_t)(uint16_t)(wpair >> (16 * (p & 1)));
-          r = (f >= cc.foot_threshold) ? 1.0f : 0.0f;
-        } else r = x;                                           // gyro, dq
-        v[e] = r;
+      for (int c = 0; c < kDof; ++c) nf[9 + c] = __double2float_rn(__dsub_rn((double)rf[7 + c], cc.q0[c]));
+#pragma unroll
+      for (int c = 0; c < kDof; ++c) nf[21 + c] = rf[19 + c];
+      if (prev_action) {
+        const float4* pa = reinterpret_cast<const float4*>(prev_action + row * kDof);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { const float4 t4 = pa[q]; nf[33 + 4 * q] = t4.x; nf[34 + 4 * q] = t4.y; nf[35 + 4 * q] = t4.z; nf[36 + 4 * q] = t4.w; }
+      } else {
+#pragma unroll
+        for (int c = 0; c < kDof; ++c) nf[33 + c] = 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int p = c ^ 1;                                       // [1,0,3,2] (controller.hpp:99-103)
+        const int force = (int)(int16_t)(uint16_t)(rw[35 + (p >> 1)] >> (16 * (p & 1)));
+        nf[45 + c] = (force >= cc.foot_threshold) ? 1.0f : 0.0f;
+      }
+      if (button0_out) button0_out[row] = (int32_t)rw[38];
+    }
+    __syncwarp();
+    // 3. shift + append, row by row, kAsmRowsInFlight rows of loads in flight
+    for (int r0 = 0; r0 < rows; r0 += kAsmRowsInFlight) {
+      float v[kAsmRowsInFlight][kPerLane];
+#pragma unroll
+      for (int i = 0; i < kAsmRowsInFlight; ++i) {
+        const int r = r0 + i;
+        if (r < rows) {
+          const float* o = obs + (row0 + r) * n_obs;
+#pragma unroll
+          for (int e = 0; e < kPerLane; ++e) {
+            const int mt = meta[e];
+            v[i][e] = mt < 0 ? 0.f : ((mt & 0x100) ? o[e * 32 + lane + (mt & 0xff)] : my_new[r * kFrame + mt]);
+          }
+        }
+      }
+      __syncwarp();      // every lane holds the old values of these rows before any lane overwrites them
+#pragma unroll
+      for (int i = 0; i < kAsmRowsInFlight; ++i) {
+        const int r = r0 + i;
+        if (r < rows) {
+          float* o = obs + (row0 + r) * n_obs;
+#pragma unroll
+          for (int e = 0; e < kPerLane; ++e)
+            if (meta[e] >= 0) o[e * 32 + lane] = v[i][e];
+        }
       }
     }
-    __syncwarp();      // every lane holds its old values before any lane overwrites them
-#pragma unroll
-    for (int e = 0; e < kPerLane; ++e)
-      if (meta[e] >= 0) o[e * 32 + lane] = v[e];
-    if (lane < 3 && joy_valid) vel_cmd[row * 3 + lane] = lane == 0 ? c0 : (lane == 1 ? c1 : c2);
-    if (lane == 6 && button0_out) button0_out[row] = (int32_t)w1;
+    __syncwarp();        // shared buffers are reused by the next group
   }
 }
 
 // n_obs = 49*H floats per row: 4 elements per lane serve H <= 2, 13 serve H <= 8
 inline void launch_assemble_batch(const RawStateDev* raw, const float* prev_action, float* vel_cmd, float* obs, long long B,
                                   const CtrlConst& cc, int32_t* button0_out, int sm_count, cudaStream_t st) {
-  const unsigned grid = (unsigned)std::min<long long>((B + kAsmWarps - 1) / kAsmWarps, (long long)sm_count * 32);
+  const long long groups = (B + 31) / 32;
+  const unsigned grid = (unsigned)std::min<long long>((groups + kAsmWarps - 1) / kAsmWarps, (long long)sm_count * 16);
   if (kFrame * cc.H <= 128)
     assemble_batch_kernel<4><<<grid, kAsmWarps * 32, 0, st>>>(raw, prev_action, vel_cmd, obs, B, cc, button0_out);
   else
