@@ -13,7 +13,7 @@
 //   * weights are packed on the host the same way per (N-tile, K-chunk);
 //   * wide_gemm_kernel: persistent CTAs over (row tile, N tile); warp 0 = producer (3-stage mbarrier ring of A/B
 //     chunks), warp 1 = MMA issuer (SS-form tcgen05.mma, M=128, N=NT, four K steps per 64-wide chunk, accumulators
-//     double-buffered in TMEM so the epilogue of one tile overlaps the MMAs of the next), warps 2-5 = epilogue
+//     double-buffered in TMEM so the epilogue of one tile overlaps the MMAs of the next), warps 2-17 = epilogue
 //     (tcgen05.ld -> +bias -> ELU -> 16-bit -> blocked store for the next layer, or the fused A9/A11 output epilogue);
 //   * obs_to_blocked_kernel converts the fp32 [B,in] observations into the blocked 16-bit layout (zero padded).
 #pragma once
@@ -33,7 +33,11 @@ constexpr int kWdTileM = 128;
 constexpr int kWdChunkK = 64;                       // K columns per pipeline stage (4 MMA K steps)
 constexpr int kWdATileBytes = kWdTileM * kWdChunkK * 2;   // 16 KB
 constexpr int kWdStages = 4;                        // 4 x 48 KB (N tile 256) = 192 KB of operands in flight per SM
-constexpr int kWdEpiWarps = 8;                      // two per TMEM lane quarter, each takes half of the tile's columns
+#ifndef GO2P_WD_EPI_WARPS
+#define GO2P_WD_EPI_WARPS 16
+#endif
+constexpr int kWdEpiWarps = GO2P_WD_EPI_WARPS;      // kWdEpiWarps/4 per TMEM lane quarter, each takes a share of the tile's columns
+constexpr int kWdEpiParts = kWdEpiWarps / 4;
 constexpr int kWdThreads = (2 + kWdEpiWarps) * 32;  // producer, MMA issuer, epilogue warps
 
 // byte offset of element (r, c) inside a [rows x 64] blocked tile (rows multiple of 8)
@@ -181,7 +185,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemm
   } else {
     // ================= epilogue warps (lane quarter = warp % 4) =================
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;                // which half of the N tile's columns this warp converts
+    const int half = (warp - 2) >> 2;                // which share of the N tile's columns this warp converts
     const uint32_t lane_addr = ((uint32_t)(quarter * 32)) << 16;
     const int r = quarter * 32 + lane;               // row inside the tile
     uint32_t tile_i = 0;
@@ -197,8 +201,9 @@ __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemm
         // hidden layer: 32 columns at a time -> bias + ELU -> 16 bit -> four 16-byte stores into the next layer's tile
         const int kcn_per_tile = NT / kWdChunkK;       // 64-column chunks of the next layer covered by this N tile
         const long long next_chunks = (long long)a.n_tiles * kcn_per_tile;
+        constexpr int kShare = (NT / kWdEpiParts) < 32 ? 32 : (NT / kWdEpiParts);   // columns per warp, whole 32-column groups
 #pragma unroll 1
-        for (int c0 = half * (NT / 2); c0 < (half + 1) * (NT / 2); c0 += 32) {
+        for (int c0 = half * kShare; c0 < (half + 1) * kShare && c0 < NT; c0 += 32) {
           uint32_t v[32];
           ptx::tmem_ld_x32(acc_t + (uint32_t)c0, v);
           ptx::tc_wait_ld();
@@ -319,8 +324,14 @@ inline int wide_prepare(const MlpModel& m, std::vector<void*>& dev_owned, WideMo
 template <int NT, bool kFp16>
 inline cudaError_t wd_launch_gemm(const WideGemmArgs& a, int sm_count, cudaStream_t st) {
   const size_t smem = (size_t)kWdStages * (kWdATileBytes + NT * kWdChunkK * 2) + 256;
-  cudaError_t e = cudaFuncSetAttribute(wide_gemm_kernel<NT, kFp16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  static thread_local int configured_dev = -1;           // the attribute is per device and per function
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(wide_gemm_kernel<NT, kFp16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured_dev = dev;
+  }
   const long long jobs = (long long)a.m_tiles * a.n_tiles;
   const int grid = (int)std::min<long long>(jobs, sm_count);
   wide_gemm_kernel<NT, kFp16><<<grid, kWdThreads, smem, st>>>(a);
