@@ -15,18 +15,19 @@
 //     tcgen05.ld, apply ELU, pack to 16 bit and write the result back IN PLACE (the first 16 columns of
 //     every 32-column block) with tcgen05.st, where the next layer's tcgen05.mma reads it as its A
 //     operand (TS form) while accumulating into the other buffer.  The activation never leaves the SM;
-//   * A-operand readiness is tracked per 32-column block (one mbarrier each), so the next layer's K steps
-//     are issued while the epilogue is still working on later blocks: the MMA trails the epilogue instead
-//     of starting after it;
+//   * A-operand readiness is tracked per 32-column block (one mbarrier each, 4 arrivals = 4 lane quarters); the
+//     slot's control warp waits for the four blocks and issues the layer's K steps back to back in a fixed order,
+//     so the fp32 accumulation order (every output bit) does not depend on timing;
 //   * the bias rides inside the MMA: every A operand carries two constant 1.0 columns and the weight
 //     matrix two extra K rows holding hi/lo halves of the bias, so the epilogue has no bias add;
 //   * the chain is evaluated in the base-2 exponent domain: layer l produces z' = log2(e)*z, the ELU is
-//     h' = z' > 0 ? z' : c*(2^z' - 1) with c = alpha*log2(e) (one MUFU.EX2 + one FFMA), h' = log2(e)*h
-//     feeds the next layer whose weights carry the inverse factor (folded on the host);
-//   * the ELU select runs on packed 16-bit pairs (HSET2 + LOP3), so an element costs
-//     1 MUFU + 1 FFMA + 2 ALU instructions; the MUFU pipe (16 lanes/clk/SM) is the per-SM floor;
-//   * one elected thread issues every tcgen05.mma and signals completion with tcgen05.commit; while the
-//     tensor core works on one slot the 8 epilogue warps of the other slot keep the MUFU pipe busy.
+//     h' = z' > 0 ? z' : c*(2^z' - 1) with c = alpha*log2(e), h' = log2(e)*h feeds the next layer whose weights
+//     carry the inverse factor (folded on the host);
+//   * fp16 path: the ELU runs on packed pairs -- F2FP (pack z'), ex2.approx.f16x2 (2 MUFU + PRMT), one HFMA2
+//     (c*e - c), HSET2 + LOP3 select: 7 instructions per pair; one pair in eight takes a polynomial 2^x on the FMA
+//     pipe instead of the MUFU (16 lanes/clk/SM).  bf16 keeps the fp32 exponential;
+//   * one elected thread issues every tcgen05.mma and signals completion with tcgen05.commit; ONE pool of 16 worker
+//     warps walks the jobs of both slots alternately, so a slot's MMAs run while the pool works on the other slot.
 #pragma once
 #include "policy_dev.cuh"
 #include "ptx_sm100.cuh"
