@@ -223,29 +223,62 @@ MlpModel parse_onnx_mlp(const uint8_t* data, size_t size) {
   m.output_shape = outputs[0].shape;
 
   std::string cur = m.input_name;
+  bool bias_open = false;      // the last layer came from a MatMul / bias-less Gemm and may still take an Add
+  auto add_layer = [&](const Node& n, const Tensor& W, bool w_is_out_in, const Tensor* Bv) {
+    if (W.dims.size() != 2) fail("node '" + n.name + "': weight must be 2-D");
+    MlpLayer L;
+    L.out = int(w_is_out_in ? W.dims[0] : W.dims[1]);
+    L.in = int(w_is_out_in ? W.dims[1] : W.dims[0]);
+    if (int64_t(W.data.size()) != int64_t(L.out) * L.in) fail("node '" + n.name + "': weight data does not match its dims");
+    if (Bv && int64_t(Bv->data.size()) != L.out) fail("node '" + n.name + "': bias length does not match weight");
+    if (!m.layers.empty() && m.layers.back().out != L.in) fail("node '" + n.name + "': inner dimension mismatch");
+    L.weight.resize(size_t(L.out) * L.in);
+    for (int o = 0; o < L.out; ++o)
+      for (int k = 0; k < L.in; ++k)
+        L.weight[size_t(o) * L.in + k] = w_is_out_in ? W.data[size_t(o) * L.in + k] : W.data[size_t(k) * L.out + o];
+    if (Bv) L.bias = Bv->data; else L.bias.assign(size_t(L.out), 0.0f);
+    m.layers.push_back(std::move(L));
+  };
   for (const Node& n : nodes) {
     if (n.op == "Gemm") {
-      if (n.inputs.size() != 3 || n.inputs[0] != cur) fail("node '" + n.name + "': Gemm is not chained on '" + cur + "' (with bias)");
+      if ((n.inputs.size() != 3 && n.inputs.size() != 2) || n.inputs[0] != cur)
+        fail("node '" + n.name + "': Gemm is not chained on '" + cur + "'");
       auto fa = [&](const char* k, float d) { auto it = n.fattr.find(k); return it == n.fattr.end() ? d : it->second; };
       auto ia = [&](const char* k, int64_t d) { auto it = n.iattr.find(k); return it == n.iattr.end() ? d : it->second; };
       if (fa("alpha", 1.f) != 1.f || fa("beta", 1.f) != 1.f) fail("node '" + n.name + "': only alpha = beta = 1 is supported");
       if (ia("transA", 0) != 0) fail("node '" + n.name + "': transA = 1 is not supported");
-      auto wi = inits.find(n.inputs[1]), bi = inits.find(n.inputs[2]);
-      if (wi == inits.end() || bi == inits.end()) fail("node '" + n.name + "': weight/bias must be initializers");
-      const Tensor& W = wi->second; const Tensor& B = bi->second;
-      if (W.dims.size() != 2) fail("node '" + n.name + "': weight must be 2-D");
-      const bool tb = ia("transB", 0) != 0;
-      MlpLayer L;
-      L.out = int(tb ? W.dims[0] : W.dims[1]);
-      L.in = int(tb ? W.dims[1] : W.dims[0]);
-      if (int64_t(B.data.size()) != L.out) fail("node '" + n.name + "': bias length does not match weight");
-      if (!m.layers.empty() && m.layers.back().out != L.in) fail("node '" + n.name + "': inner dimension mismatch");
-      L.weight.resize(size_t(L.out) * L.in);
-      for (int o = 0; o < L.out; ++o)
-        for (int k = 0; k < L.in; ++k)
-          L.weight[size_t(o) * L.in + k] = tb ? W.data[size_t(o) * L.in + k] : W.data[size_t(k) * L.out + o];
-      L.bias = B.data;
-      m.layers.push_back(std::move(L));
+      auto wi = inits.find(n.inputs[1]);
+      if (wi == inits.end()) fail("node '" + n.name + "': weight must be an initializer");
+      const Tensor* Bv = nullptr;
+      if (n.inputs.size() == 3) {
+        auto bi = inits.find(n.inputs[2]);
+        if (bi == inits.end()) fail("node '" + n.name + "': bias must be an initializer");
+        Bv = &bi->second;
+      }
+      add_layer(n, wi->second, ia("transB", 0) != 0, Bv);
+      bias_open = Bv == nullptr;
+      cur = n.output;
+    } else if (n.op == "MatMul") {
+      // x @ W with W [in, out] (what exporters emit for Linear layers on >2-D inputs); an Add may supply the bias
+      if (n.inputs.size() != 2 || n.inputs[0] != cur) fail("node '" + n.name + "': MatMul is not chained on '" + cur + "'");
+      auto wi = inits.find(n.inputs[1]);
+      if (wi == inits.end()) fail("node '" + n.name + "': MatMul weight must be an initializer");
+      add_layer(n, wi->second, false, nullptr);
+      bias_open = true;
+      cur = n.output;
+    } else if (n.op == "Add") {
+      if (n.inputs.size() != 2 || !bias_open || m.layers.empty())
+        fail("node '" + n.name + "': Add is only supported as the bias of the preceding MatMul / bias-less Gemm");
+      const std::string& other = n.inputs[0] == cur ? n.inputs[1] : n.inputs[0];
+      if (n.inputs[0] != cur && n.inputs[1] != cur) fail("node '" + n.name + "': Add is not chained on '" + cur + "'");
+      auto bi = inits.find(other);
+      if (bi == inits.end() || int64_t(bi->second.data.size()) != m.layers.back().out)
+        fail("node '" + n.name + "': Add operand must be an initializer of the layer's output width");
+      m.layers.back().bias = bi->second.data;
+      bias_open = false;
+      cur = n.output;
+    } else if (n.op == "Identity") {
+      if (n.inputs.size() != 1 || n.inputs[0] != cur) fail("node '" + n.name + "': Identity is not chained on '" + cur + "'");
       cur = n.output;
     } else if (n.op == "Elu") {
       if (m.layers.empty() || n.inputs.size() != 1 || n.inputs[0] != cur || m.layers.back().has_elu)
@@ -253,9 +286,10 @@ MlpModel parse_onnx_mlp(const uint8_t* data, size_t size) {
       auto it = n.fattr.find("alpha");
       m.layers.back().has_elu = true;
       m.layers.back().elu_alpha = it == n.fattr.end() ? 1.0f : it->second;
+      bias_open = false;
       cur = n.output;
     } else {
-      fail("node '" + n.name + "': unsupported op_type '" + n.op + "' (supported: Gemm, Elu)");
+      fail("node '" + n.name + "': unsupported op_type '" + n.op + "' (supported: Gemm, MatMul, Add, Elu, Identity)");
     }
   }
   if (m.layers.empty()) fail("graph has no Gemm node");

@@ -271,30 +271,58 @@ def load_policy(path_or_bytes) -> Policy:
         raise ValueError("expected exactly one graph input and one graph output")
     cur = graph_inputs[0].name
     layers = []
+    bias_open = False          # last layer came from MatMul / bias-less Gemm and may still take an Add
+
+    def add_layer(n, w, b):
+        if w.ndim != 2:
+            raise ValueError(f"node '{n.name}': weight must be 2-D")
+        if b is None:
+            b = np.zeros(w.shape[0], np.float32)
+        if b.shape != (w.shape[0],):
+            raise ValueError(f"node '{n.name}': bias shape {b.shape} vs weight {w.shape}")
+        if layers and layers[-1].weight.shape[0] != w.shape[1]:
+            raise ValueError(f"node '{n.name}': inner dimension mismatch")
+        layers.append(Layer(np.ascontiguousarray(w, np.float32), np.ascontiguousarray(b, np.float32), None))
+
     for n in nodes:
         if n.op_type == "Gemm":
-            if len(n.inputs) != 3 or n.inputs[0] != cur:
+            if len(n.inputs) not in (2, 3) or n.inputs[0] != cur:
                 raise ValueError(f"node '{n.name}': Gemm is not chained on '{cur}'")
             if n.attrs.get("alpha", 1.0) != 1.0 or n.attrs.get("beta", 1.0) != 1.0:
                 raise ValueError(f"node '{n.name}': only alpha=beta=1 Gemm is supported")
             if n.attrs.get("transA", 0) != 0:
                 raise ValueError(f"node '{n.name}': transA=1 is not supported")
             w = inits[n.inputs[1]]
-            b = inits[n.inputs[2]]
-            if w.ndim != 2:
-                raise ValueError(f"node '{n.name}': weight must be 2-D")
-            if n.attrs.get("transB", 0) == 0:
+            if w.ndim == 2 and n.attrs.get("transB", 0) == 0:
                 w = np.ascontiguousarray(w.T)
-            if b.shape != (w.shape[0],):
-                raise ValueError(f"node '{n.name}': bias shape {b.shape} vs weight {w.shape}")
-            if layers and layers[-1].weight.shape[0] != w.shape[1]:
-                raise ValueError(f"node '{n.name}': inner dimension mismatch")
-            layers.append(Layer(np.ascontiguousarray(w, np.float32), np.ascontiguousarray(b, np.float32), None))
+            add_layer(n, w, inits[n.inputs[2]] if len(n.inputs) == 3 else None)
+            bias_open = len(n.inputs) == 2
+            cur = n.outputs[0]
+        elif n.op_type == "MatMul":
+            if len(n.inputs) != 2 or n.inputs[0] != cur or n.inputs[1] not in inits:
+                raise ValueError(f"node '{n.name}': MatMul is not chained on '{cur}' with an initializer weight")
+            w = inits[n.inputs[1]]
+            add_layer(n, np.ascontiguousarray(w.T) if w.ndim == 2 else w, None)
+            bias_open = True
+            cur = n.outputs[0]
+        elif n.op_type == "Add":
+            if len(n.inputs) != 2 or not bias_open or not layers or cur not in n.inputs:
+                raise ValueError(f"node '{n.name}': Add is only supported as the bias of the preceding MatMul")
+            other = n.inputs[1] if n.inputs[0] == cur else n.inputs[0]
+            if other not in inits or inits[other].shape != (layers[-1].weight.shape[0],):
+                raise ValueError(f"node '{n.name}': Add operand must be an initializer of the layer's output width")
+            layers[-1].bias = np.ascontiguousarray(inits[other], np.float32)
+            bias_open = False
+            cur = n.outputs[0]
+        elif n.op_type == "Identity":
+            if len(n.inputs) != 1 or n.inputs[0] != cur:
+                raise ValueError(f"node '{n.name}': Identity is not chained on '{cur}'")
             cur = n.outputs[0]
         elif n.op_type == "Elu":
             if not layers or n.inputs[0] != cur or layers[-1].elu_alpha is not None:
                 raise ValueError(f"node '{n.name}': Elu must directly follow a Gemm")
             layers[-1].elu_alpha = float(n.attrs.get("alpha", 1.0))
+            bias_open = False
             cur = n.outputs[0]
         else:
             raise ValueError(f"node '{n.name}': unsupported op_type '{n.op_type}'")
@@ -370,7 +398,7 @@ def _value_info(name: str, shape) -> bytes:
 def write_mlp_onnx(weights, biases, elu_alpha=1.0, *, batch=1, trans_b=True,
                    packed_dims=False, use_float_data=False,
                    input_name="observation", output_name="action",
-                   final_activation=False) -> bytes:
+                   final_activation=False, form="gemm", identity_tail=False) -> bytes:
     """Serialise a Gemm/Elu MLP the way torch.onnx.export names things.
 
     weights[i] is [out, in].  ``batch`` may be an int or a symbolic dim string.
@@ -382,7 +410,27 @@ def write_mlp_onnx(weights, biases, elu_alpha=1.0, *, batch=1, trans_b=True,
         idx = 2 * i
         wname, bname = f"{idx}.weight", f"{idx}.bias"
         last = i == n - 1
-        gemm_out = output_name if (last and not final_activation) else f"/{idx}/Gemm_output_0"
+        tail_name = output_name if not identity_tail else "/tail/Identity_input"
+        gemm_out = tail_name if (last and not final_activation) else f"/{idx}/Gemm_output_0"
+        if form == "matmul_add" or (form == "mixed" and i % 2 == 1):
+            # x @ W[in,out] followed by Add(bias): the other way exporters spell a Linear layer
+            mm_out = f"/{idx}/MatMul_output_0"
+            node = (_ld(1, cur.encode()) + _ld(1, wname.encode()) + _ld(2, mm_out.encode())
+                    + _ld(3, f"/{idx}/MatMul".encode()) + _ld(4, b"MatMul"))
+            nodes += _ld(1, node)
+            node = (_ld(1, bname.encode()) + _ld(1, mm_out.encode()) + _ld(2, gemm_out.encode())
+                    + _ld(3, f"/{idx}/Add".encode()) + _ld(4, b"Add"))
+            nodes += _ld(1, node)
+            inits += _ld(5, _tensor(wname, np.ascontiguousarray(np.asarray(w, np.float32).T), packed_dims, use_float_data))
+            inits += _ld(5, _tensor(bname, np.asarray(b, np.float32), packed_dims, use_float_data))
+            cur = gemm_out
+            if not last or final_activation:
+                elu_out = tail_name if last else f"/{idx + 1}/Elu_output_0"
+                node = (_ld(1, cur.encode()) + _ld(2, elu_out.encode()) + _ld(3, f"/{idx + 1}/Elu".encode())
+                        + _ld(4, b"Elu") + _ld(5, _ld(1, b"alpha") + _f32(2, float(elu_alpha)) + _vi(20, 1)))
+                nodes += _ld(1, node)
+                cur = elu_out
+            continue
         node = (_ld(1, cur.encode()) + _ld(1, wname.encode()) + _ld(1, bname.encode())
                 + _ld(2, gemm_out.encode()) + _ld(3, f"/{idx}/Gemm".encode()) + _ld(4, b"Gemm")
                 + _ld(5, _ld(1, b"alpha") + _f32(2, 1.0) + _vi(20, 1))
@@ -394,11 +442,13 @@ def write_mlp_onnx(weights, biases, elu_alpha=1.0, *, batch=1, trans_b=True,
         inits += _ld(5, _tensor(bname, np.asarray(b, np.float32), packed_dims, use_float_data))
         cur = gemm_out
         if not last or final_activation:
-            elu_out = output_name if last else f"/{idx + 1}/Elu_output_0"
+            elu_out = tail_name if last else f"/{idx + 1}/Elu_output_0"
             node = (_ld(1, cur.encode()) + _ld(2, elu_out.encode()) + _ld(3, f"/{idx + 1}/Elu".encode())
                     + _ld(4, b"Elu") + _ld(5, _ld(1, b"alpha") + _f32(2, float(elu_alpha)) + _vi(20, 1)))
             nodes += _ld(1, node)
             cur = elu_out
+    if identity_tail:
+        nodes += _ld(1, _ld(1, cur.encode()) + _ld(2, output_name.encode()) + _ld(3, b"/tail/Identity") + _ld(4, b"Identity"))
     in_dim = int(np.asarray(weights[0]).shape[1])
     out_dim = int(np.asarray(weights[-1]).shape[0])
     graph = (nodes + _ld(2, b"main_graph") + inits

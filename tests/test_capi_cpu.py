@@ -83,6 +83,28 @@ def test_unsupported_op_is_rejected(lib, tmp_path):
     assert rc == capi.ERR_MODEL and "Erf" in msg
 
 
+@pytest.mark.skipif(not _no_gpu(), reason="uses the no-device error to tell 'parsed' from 'rejected'")
+@pytest.mark.parametrize("form,tail", [("matmul_add", False), ("mixed", True), ("gemm", True)])
+def test_other_spellings_of_linear_layers_parse(lib, tmp_path, form, tail):
+    """MatMul + Add, bias-less Gemm and a trailing Identity are accepted by the reader (the graph parses, so the
+    create call gets as far as the device check); a stray Add is still rejected with a message."""
+    rng = np.random.default_rng(1)
+    ws = [rng.normal(0, 1, (8, 5)).astype(np.float32), rng.normal(0, 1, (3, 8)).astype(np.float32)]
+    bs = [rng.normal(0, 1, 8).astype(np.float32), rng.normal(0, 1, 3).astype(np.float32)]
+    p = tmp_path / "m.onnx"
+    p.write_bytes(onnx_mini.write_mlp_onnx(ws, bs, 1.0, form=form, identity_tail=tail))
+    rc, h, msg = _create(lib, p)
+    assert rc == capi.ERR_NO_DEVICE, msg
+    pol = onnx_mini.load_policy(os.fspath(p))
+    assert all(np.array_equal(l.weight, w) and np.array_equal(l.bias, b) for l, w, b in zip(pol.layers, ws, bs))
+    # an Add that is not the bias of the preceding MatMul
+    bad = onnx_mini.write_mlp_onnx(ws, bs, 1.0, form="matmul_add").replace(b"MatMul", b"Gemm\x00\x00")
+    q = tmp_path / "bad.onnx"
+    q.write_bytes(bad)
+    rc, h, msg = _create(lib, q)
+    assert rc == capi.ERR_MODEL and msg
+
+
 def test_struct_size_mismatch_is_invalid(lib, model_path):
     cfg = actor.default_config()
     cfg.struct_size = 8

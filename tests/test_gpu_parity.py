@@ -485,6 +485,26 @@ def test_other_narrow_policies_all_paths(torch_cuda, tmp_path, shape):
         p.close()
 
 
+def test_matmul_add_spelling_gives_identical_bits(torch_cuda, tmp_path, policy):
+    """The same weights written as Gemm or as MatMul + Add (+ trailing Identity) are the same policy to the kernels."""
+    from oracle import onnx_mini
+    ws = [l.weight for l in policy.layers]
+    bs = [l.bias for l in policy.layers]
+    X = oracle.make_obs_d1(777, 98, seed=12)
+    outs = []
+    for form, tail in (("gemm", False), ("matmul_add", True), ("mixed", False)):
+        path = tmp_path / f"{form}.onnx"
+        path.write_bytes(onnx_mini.write_mlp_onnx(ws, bs, policy.layers[0].elu_alpha, form=form, identity_tail=tail))
+        p = PolicyBatch(str(path))
+        try:
+            outs.append([run_batch(torch_cuda, p, X, prec)[0] for prec in (capi.PREC_FP32, capi.PREC_FP16)])
+        finally:
+            p.close()
+    for o in outs[1:]:
+        assert np.array_equal(bits(o[0]), bits(outs[0][0])) and np.array_equal(bits(o[1]), bits(outs[0][1]))
+    assert_fp32_parity(outs[0][0].astype(np.float64), oracle.forward(policy, X, np.float64))
+
+
 def test_wide_policy_fp32_path(torch_cuda, wide_model_path):
     """BASELINE.json configs[4]: synthetic 245-1024-512-256-12 ELU policy (5-frame history input)."""
     cm = coracle.CModel(wide_model_path)
