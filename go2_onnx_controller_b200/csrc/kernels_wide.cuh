@@ -107,7 +107,12 @@ __global__ void obs_to_blocked_kernel(const float* __restrict__ obs, uint16_t* _
   }
 }
 
-template <int NT, bool kFp16>
+// kCS = thread-block cluster size (1 or 2).  With kCS = 2 the two CTAs of a cluster work on neighbouring row tiles of
+// the SAME N tile: each loads its own A tile and HALF of the weight tile, which the TMA engine multicasts into both
+// CTAs' shared memory -- the weight tile crosses the L2 -> SM fabric once per cluster instead of once per CTA (32 KB
+// instead of 48 KB of operand traffic per CTA and K chunk at NT = 256).  A stage is refilled only when the MMAs of
+// BOTH CTAs have read it: tcgen05.commit arrives on the stage's empty barrier of every CTA in the cluster.
+template <int NT, bool kFp16, int kCS>
 __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemmArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int kBTileBytes = NT * kWdChunkK * 2;
@@ -124,7 +129,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemm
 
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < kWdStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+      for (int s = 0; s < kWdStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], kCS); }
       for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], kWdEpiWarps); }
       ptx::fence_mbar_init();
     }
@@ -133,15 +138,25 @@ __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemm
   }
   ptx::tc_fence_before();
   block_sync();
+  if (kCS > 1) ptx::cluster_sync_all();     // the peer's barriers exist before anything is multicast into them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const long long n_jobs = (long long)a.m_tiles * a.n_tiles;     // job = (row tile, N tile), N tile fastest: A stays in L2
+  // job = (group of kCS row tiles, N tile), N tile fastest: the A tiles stay in L2 for the next N tile.
+  // Every CTA of a cluster walks the same job list; CTA rank r takes row tile group*kCS + r.  A rank whose row tile
+  // does not exist (odd tile count) still loads and multiplies a clamped tile -- its half of the weights is needed by
+  // the peer -- and only skips the stores.
+  const uint32_t crank = kCS > 1 ? ptx::cluster_ctarank() : 0u;
+  const long long job0 = kCS > 1 ? (long long)ptx::cluster_id_x() : (long long)blockIdx.x;
+  const long long job_stride = kCS > 1 ? (long long)ptx::cluster_nctaid_x() : (long long)gridDim.x;
+  const long long m_groups = (a.m_tiles + kCS - 1) / kCS;
+  const long long n_jobs = m_groups * a.n_tiles;
+  auto job_mt = [&](long long job) { return (job / a.n_tiles) * kCS + crank; };
   if (warp == 0) {
     // ================= producer =================
     uint32_t it = 0;
-    for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x) {
-      const long long mt = job / a.n_tiles;
+    for (long long job = job0; job < n_jobs; job += job_stride) {
+      const long long mt = min(job_mt(job), (long long)a.m_tiles - 1);
       const int nt = (int)(job % a.n_tiles);
       for (int kc = 0; kc < a.k_chunks; ++kc, ++it) {
         const int s = it % kWdStages;
@@ -150,8 +165,13 @@ __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemm
           uint8_t* st = smem + s * kStageBytes;
           ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)kStageBytes);
           ptx::bulk_g2s(st, reinterpret_cast<const uint8_t*>(a.a) + (mt * a.k_chunks + kc) * (long long)kWdATileBytes, kWdATileBytes, &full[s]);
-          ptx::bulk_g2s(st + kWdATileBytes, reinterpret_cast<const uint8_t*>(a.w) + ((long long)nt * a.k_chunks + kc) * (long long)kBTileBytes,
-                        kBTileBytes, &full[s]);
+          const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w) + ((long long)nt * a.k_chunks + kc) * (long long)kBTileBytes;
+          if (kCS > 1) {
+            constexpr uint32_t kPart = kBTileBytes / kCS;     // whole 8-row groups: a contiguous slice of the tile
+            ptx::bulk_g2s_multicast(st + kWdATileBytes + crank * kPart, wsrc + crank * kPart, kPart, &full[s], (uint16_t)((1u << kCS) - 1u));
+          } else {
+            ptx::bulk_g2s(st + kWdATileBytes, wsrc, kBTileBytes, &full[s]);
+          }
         }
         __syncwarp();
       }
@@ -160,7 +180,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemm
     // ================= MMA issuer =================
     const uint32_t idesc = ptx::make_idesc(kFp16 ? ptx::FMT_F16 : ptx::FMT_BF16, kWdTileM, (uint32_t)NT);
     uint32_t it = 0, tile_i = 0;
-    for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x, ++tile_i) {
+    for (long long job = job0; job < n_jobs; job += job_stride, ++tile_i) {
       const uint32_t buf = tile_i & 1u;
       ptx::mbar_wait(&acc_empty[buf], ((tile_i >> 1) & 1u) ^ 1u);
       ptx::tc_fence_after();
@@ -176,7 +196,8 @@ __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemm
 #pragma unroll
           for (int j = 0; j < kWdChunkK / 16; ++j)
             ptx::mma_f16_ss(d_t, adesc + (uint64_t)(j * 16), bdesc + (uint64_t)(j * 16), idesc, (kc | j) ? 1u : 0u);
-          ptx::mma_commit(&empty[s]);                       // frees the stage when these MMAs have read it
+          // frees the stage (in every CTA of the cluster) when these MMAs have read it
+          if (kCS > 1) ptx::mma_commit_multicast(&empty[s], (uint16_t)((1u << kCS) - 1u)); else ptx::mma_commit(&empty[s]);
           if (kc == a.k_chunks - 1) ptx::mma_commit(&acc_full[buf]);
         }
         __syncwarp();
@@ -189,15 +210,18 @@ __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemm
     const uint32_t lane_addr = ((uint32_t)(quarter * 32)) << 16;
     const int r = quarter * 32 + lane;               // row inside the tile
     uint32_t tile_i = 0;
-    for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x, ++tile_i) {
-      const long long mt = job / a.n_tiles;
+    for (long long job = job0; job < n_jobs; job += job_stride, ++tile_i) {
+      const long long mt = job_mt(job);
+      const bool ghost = mt >= a.m_tiles;              // clamped duplicate of the last row tile: no stores
       const int nt = (int)(job % a.n_tiles);
       const uint32_t buf = tile_i & 1u;
       ptx::mbar_wait(&acc_full[buf], (tile_i >> 1) & 1u);
       ptx::tc_fence_after();
       const uint32_t acc_t = tmem_base + buf * kAccCols + lane_addr;
       const long long row = mt * kWdTileM + r;
-      if (a.out_blocked) {
+      if (ghost) {
+        // nothing to store; the accumulator is simply released
+      } else if (a.out_blocked) {
         // hidden layer: 32 columns at a time -> bias + ELU -> 16 bit -> four 16-byte stores into the next layer's tile
         const int kcn_per_tile = NT / kWdChunkK;       // 64-column chunks of the next layer covered by this N tile
         const long long next_chunks = (long long)a.n_tiles * kcn_per_tile;
@@ -256,6 +280,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemm
 
   ptx::tc_fence_before();
   block_sync();
+  if (kCS > 1) ptx::cluster_sync_all();     // no CTA leaves while the peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<kTmemCols>(tmem_base);
@@ -321,21 +346,50 @@ inline int wide_prepare(const MlpModel& m, std::vector<void*>& dev_owned, WideMo
   return 0;
 }
 
+// Cluster size of the GEMM launches.  Measured on B200 (scripts/gpu_wide_variants.sh): the multicast variant (2) is
+// correct (same tests) but not faster than 1 -- the kernel is limited by what ONE SM can take in from L2 (48 KB per
+// 512 tensor cycles = 96 B/clk asked, ~64 B/clk delivered), and a multicast tile still has to enter every SM.  The
+// remedy is a tile that needs fewer operand bytes per SM (cta_group::2: each SM holds half of the weight tile).
+#ifndef GO2P_WD_CLUSTER
+#define GO2P_WD_CLUSTER 1
+#endif
+
 template <int NT, bool kFp16>
 inline cudaError_t wd_launch_gemm(const WideGemmArgs& a, int sm_count, cudaStream_t st) {
+  constexpr int kCS = GO2P_WD_CLUSTER;
   const size_t smem = (size_t)kWdStages * (kWdATileBytes + NT * kWdChunkK * 2) + 256;
+  auto kernel = wide_gemm_kernel<NT, kFp16, kCS>;
   static thread_local int configured_dev = -1;           // the attribute is per device and per function
+  static thread_local int max_clusters = 0;
   int dev = 0;
   cudaGetDevice(&dev);
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(kWdThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  if (kCS > 1) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
   if (configured_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(wide_gemm_kernel<NT, kFp16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    max_clusters = sm_count / kCS;
+    if (kCS > 1) {
+      cfg.gridDim = dim3((unsigned)(sm_count / kCS * kCS));
+      int n = 0;
+      e = cudaOccupancyMaxActiveClusters(&n, kernel, &cfg);   // clusters that can be co-resident (GPC boundaries)
+      if (e != cudaSuccess) return e;
+      if (n > 0 && n < max_clusters) max_clusters = n;
+    }
     configured_dev = dev;
   }
-  const long long jobs = (long long)a.m_tiles * a.n_tiles;
-  const int grid = (int)std::min<long long>(jobs, sm_count);
-  wide_gemm_kernel<NT, kFp16><<<grid, kWdThreads, smem, st>>>(a);
-  return cudaGetLastError();
+  const long long jobs = ((long long)a.m_tiles + kCS - 1) / kCS * a.n_tiles;
+  const long long groups = std::min<long long>(jobs, (long long)max_clusters);
+  cfg.gridDim = dim3((unsigned)(groups * kCS));
+  return cudaLaunchKernelEx(&cfg, kernel, a);
 }
 
 inline void wide_release(WideModel* wm) {
