@@ -20,6 +20,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -33,6 +35,13 @@ constexpr int kWdTileM = 128;
 constexpr int kWdChunkK = 64;                       // K columns per pipeline stage (4 MMA K steps)
 constexpr int kWdATileBytes = kWdTileM * kWdChunkK * 2;   // 16 KB
 constexpr int kWdStages = 4;                        // 4 x 48 KB (N tile 256) = 192 KB of operands in flight per SM
+// operand ring depth: as many stages as fit in ~192 KB (the L2 round trip under load is ~4,000 cycles, so the bytes in
+// flight, not the stage count, set the delivered bandwidth), at most 8
+__host__ __device__ constexpr int wd_stages(int nt, bool pair) {
+  const int stage = 128 * 64 * 2 + (pair ? nt / 2 : nt) * 64 * 2;
+  const int n = (192 * 1024) / stage;
+  return n > 8 ? 8 : n;
+}
 #ifndef GO2P_WD_EPI_WARPS
 #define GO2P_WD_EPI_WARPS 16
 #endif
@@ -112,29 +121,42 @@ __global__ void obs_to_blocked_kernel(const float* __restrict__ obs, uint16_t* _
 // CTAs' shared memory -- the weight tile crosses the L2 -> SM fabric once per cluster instead of once per CTA (32 KB
 // instead of 48 KB of operand traffic per CTA and K chunk at NT = 256).  A stage is refilled only when the MMAs of
 // BOTH CTAs have read it: tcgen05.commit arrives on the stage's empty barrier of every CTA in the cluster.
-template <int NT, bool kFp16, int kCS>
+// kCS = 2 with kPair: the two CTAs form a CTA PAIR (tcgen05 cta_group::2).  One M256 x NT MMA spans both SMs: each CTA
+// holds its own 128-row A tile and HALF of the weight tile (NT/2 rows), so an SM takes in 32 KB instead of 48 KB per K
+// chunk at NT = 256 -- the remedy for the L2 -> SM intake limit of the single-CTA tile.  The leader (rank 0) issues the
+// MMAs once its own and the peer's stage have landed (the peer relays its full-barrier to the leader), and its
+// tcgen05.commit releases stages and publishes accumulators in both CTAs; both CTAs' epilogue warps report the drained
+// accumulator to the leader.
+template <int NT, bool kFp16, int kCS, bool kPair = false>
 __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemmArgs a) {
+  static_assert(!kPair || kCS == 2, "a CTA pair is a cluster of two");
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int kBTileBytes = NT * kWdChunkK * 2;
-  constexpr int kStageBytes = kWdATileBytes + kBTileBytes;
+  constexpr int kStageBytes = kWdATileBytes + (kPair ? kBTileBytes / 2 : kBTileBytes);   // pair: half of the weight tile per CTA
+  constexpr int kStages = wd_stages(NT, kPair);
   constexpr uint32_t kAccCols = NT < 32 ? 32 : NT;               // TMEM columns per accumulator buffer
   constexpr uint32_t kTmemCols = 2 * kAccCols;                   // 64 .. 512, a power of two
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWdStages * kStageBytes);
-  uint64_t* full = bars;                 // [kWdStages] chunk landed
-  uint64_t* empty = bars + kWdStages;    // [kWdStages] chunk consumed by the tensor core
-  uint64_t* acc_full = bars + 2 * kWdStages;       // [2]
-  uint64_t* acc_empty = bars + 2 * kWdStages + 2;  // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kWdStages + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full = bars;                 // [kStages] chunk landed
+  uint64_t* empty = bars + kStages;    // [kStages] chunk consumed by the tensor core
+  uint64_t* acc_full = bars + 2 * kStages;       // [2]
+  uint64_t* acc_empty = bars + 2 * kStages + 2;  // [2]
+  uint64_t* peer_full = bars + 2 * kStages + 4;  // [kStages] leader only: the peer's chunk landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 4);
 
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < kWdStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], kCS); }
-      for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], kWdEpiWarps); }
+      for (int s = 0; s < kStages; ++s) {
+        ptx::mbar_init(&full[s], 1);
+        ptx::mbar_init(&empty[s], kPair ? 1 : kCS);      // pair: one multicast commit of the leader; multicast: one per CTA
+        ptx::mbar_init(&peer_full[s], 1);
+      }
+      for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], (kPair ? 2 : 1) * kWdEpiWarps); }
       ptx::fence_mbar_init();
     }
     __syncwarp();
-    ptx::tmem_alloc<kTmemCols>(tmem_ptr);
+    if (kPair) ptx::tmem_alloc_pair<kTmemCols>(tmem_ptr); else ptx::tmem_alloc<kTmemCols>(tmem_ptr);
   }
   ptx::tc_fence_before();
   block_sync();
@@ -159,14 +181,17 @@ __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemm
       const long long mt = min(job_mt(job), (long long)a.m_tiles - 1);
       const int nt = (int)(job % a.n_tiles);
       for (int kc = 0; kc < a.k_chunks; ++kc, ++it) {
-        const int s = it % kWdStages;
-        ptx::mbar_wait(&empty[s], ((it / kWdStages) & 1u) ^ 1u);
+        const int s = it % kStages;
+        ptx::mbar_wait(&empty[s], ((it / kStages) & 1u) ^ 1u);
         if (ptx::elect_one_sync()) {
           uint8_t* st = smem + s * kStageBytes;
-          ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)kStageBytes);
+          ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(kPair ? kWdATileBytes + kBTileBytes / 2 : kStageBytes));
           ptx::bulk_g2s(st, reinterpret_cast<const uint8_t*>(a.a) + (mt * a.k_chunks + kc) * (long long)kWdATileBytes, kWdATileBytes, &full[s]);
           const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w) + ((long long)nt * a.k_chunks + kc) * (long long)kBTileBytes;
-          if (kCS > 1) {
+          if (kPair) {
+            // this CTA's NT/2 rows of the weight tile, at the same shared-memory offset in both CTAs
+            ptx::bulk_g2s(st + kWdATileBytes, wsrc + crank * (kBTileBytes / 2), kBTileBytes / 2, &full[s]);
+          } else if (kCS > 1) {
             constexpr uint32_t kPart = kBTileBytes / kCS;     // whole 8-row groups: a contiguous slice of the tile
             ptx::bulk_g2s_multicast(st + kWdATileBytes + crank * kPart, wsrc + crank * kPart, kPart, &full[s], (uint16_t)((1u << kCS) - 1u));
           } else {
@@ -177,30 +202,45 @@ __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemm
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    const uint32_t idesc = ptx::make_idesc(kFp16 ? ptx::FMT_F16 : ptx::FMT_BF16, kWdTileM, (uint32_t)NT);
+    // ================= MMA issuer (pair mode: leader only; the peer's warp relays its full barriers) =================
+    const uint32_t idesc = ptx::make_idesc(kFp16 ? ptx::FMT_F16 : ptx::FMT_BF16, kPair ? 2 * kWdTileM : kWdTileM, (uint32_t)NT);
     uint32_t it = 0, tile_i = 0;
-    for (long long job = job0; job < n_jobs; job += job_stride, ++tile_i) {
-      const uint32_t buf = tile_i & 1u;
-      ptx::mbar_wait(&acc_empty[buf], ((tile_i >> 1) & 1u) ^ 1u);
-      ptx::tc_fence_after();
-      const uint32_t d_t = tmem_base + buf * kAccCols;
-      for (int kc = 0; kc < a.k_chunks; ++kc, ++it) {
-        const int s = it % kWdStages;
-        ptx::mbar_wait(&full[s], (it / kWdStages) & 1u);
-        ptx::tc_fence_after();
-        if (ptx::elect_one_sync()) {
-          const uint32_t sa = ptx::smem_u32(smem + s * kStageBytes);
-          const uint64_t adesc = ptx::make_smem_desc_nosw(sa, 128u, 1024u);
-          const uint64_t bdesc = ptx::make_smem_desc_nosw(sa + kWdATileBytes, 128u, 1024u);
-#pragma unroll
-          for (int j = 0; j < kWdChunkK / 16; ++j)
-            ptx::mma_f16_ss(d_t, adesc + (uint64_t)(j * 16), bdesc + (uint64_t)(j * 16), idesc, (kc | j) ? 1u : 0u);
-          // frees the stage (in every CTA of the cluster) when these MMAs have read it
-          if (kCS > 1) ptx::mma_commit_multicast(&empty[s], (uint16_t)((1u << kCS) - 1u)); else ptx::mma_commit(&empty[s]);
-          if (kc == a.k_chunks - 1) ptx::mma_commit(&acc_full[buf]);
+    if (kPair && crank != 0) {
+      for (long long job = job0; job < n_jobs; job += job_stride)
+        for (int kc = 0; kc < a.k_chunks; ++kc, ++it) {
+          const int s = it % kStages;
+          ptx::mbar_wait(&full[s], (it / kStages) & 1u);
+          if (lane == 0) ptx::mbar_arrive_cluster(&peer_full[s], 0u);
+          __syncwarp();
         }
-        __syncwarp();
+    } else {
+      for (long long job = job0; job < n_jobs; job += job_stride, ++tile_i) {
+        const uint32_t buf = tile_i & 1u;
+        ptx::mbar_wait(&acc_empty[buf], ((tile_i >> 1) & 1u) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_t = tmem_base + buf * kAccCols;
+        for (int kc = 0; kc < a.k_chunks; ++kc, ++it) {
+          const int s = it % kStages;
+          ptx::mbar_wait(&full[s], (it / kStages) & 1u);
+          if (kPair) ptx::mbar_wait(&peer_full[s], (it / kStages) & 1u);
+          ptx::tc_fence_after();
+          if (ptx::elect_one_sync()) {
+            const uint32_t sa = ptx::smem_u32(smem + s * kStageBytes);
+            const uint64_t adesc = ptx::make_smem_desc_nosw(sa, 128u, 1024u);
+            const uint64_t bdesc = ptx::make_smem_desc_nosw(sa + kWdATileBytes, 128u, 1024u);
+#pragma unroll
+            for (int j = 0; j < kWdChunkK / 16; ++j) {
+              if (kPair) ptx::mma_f16_ss_pair(d_t, adesc + (uint64_t)(j * 16), bdesc + (uint64_t)(j * 16), idesc, (kc | j) ? 1u : 0u);
+              else ptx::mma_f16_ss(d_t, adesc + (uint64_t)(j * 16), bdesc + (uint64_t)(j * 16), idesc, (kc | j) ? 1u : 0u);
+            }
+            // frees the stage (in every CTA of the cluster) when these MMAs have read it
+            if (kPair) ptx::mma_commit_pair(&empty[s], 3);
+            else if (kCS > 1) ptx::mma_commit_multicast(&empty[s], (uint16_t)((1u << kCS) - 1u));
+            else ptx::mma_commit(&empty[s]);
+            if (kc == a.k_chunks - 1) { if (kPair) ptx::mma_commit_pair(&acc_full[buf], 3); else ptx::mma_commit(&acc_full[buf]); }
+          }
+          __syncwarp();
+        }
       }
     }
   } else {
@@ -274,7 +314,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemm
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+      if (lane == 0) { if (kPair) ptx::mbar_arrive_cluster(&acc_empty[buf], 0u); else ptx::mbar_arrive(&acc_empty[buf]); }
     }
   }
 
@@ -283,7 +323,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemm
   if (kCS > 1) ptx::cluster_sync_all();     // no CTA leaves while the peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<kTmemCols>(tmem_base);
+    if (kPair) ptx::tmem_dealloc_pair<kTmemCols>(tmem_base); else ptx::tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
@@ -346,19 +386,21 @@ inline int wide_prepare(const MlpModel& m, std::vector<void*>& dev_owned, WideMo
   return 0;
 }
 
-// Cluster size of the GEMM launches.  Measured on B200 (scripts/gpu_wide_variants.sh): the multicast variant (2) is
-// correct (same tests) but not faster than 1 -- the kernel is limited by what ONE SM can take in from L2 (48 KB per
-// 512 tensor cycles = 96 B/clk asked, ~64 B/clk delivered), and a multicast tile still has to enter every SM.  The
-// remedy is a tile that needs fewer operand bytes per SM (cta_group::2: each SM holds half of the weight tile).
+// Launch mode of the GEMM kernels: 1 = one CTA per tile (default), 2 = cluster of two with TMA multicast of the weight
+// tile, 3 = CTA pair (tcgen05 cta_group::2, M256 tiles).  All three pass the same tests.  Measured on B200
+// (scripts/gpu_wide_variants.sh, 606,208 rows): 1: 2.25 ms, 2: 2.41 ms, 3: 3.19 ms.  ncu: mode 3 does cut the L2 -> SM
+// bytes by a third (233 -> 155 MB in layer 2) but its MMAs retire at a quarter of the single-CTA rate -- the
+// leader/peer hand-offs (full-barrier relay, multicast commits) sit in the per-chunk critical path; round-2 work.
 #ifndef GO2P_WD_CLUSTER
 #define GO2P_WD_CLUSTER 1
 #endif
 
 template <int NT, bool kFp16>
 inline cudaError_t wd_launch_gemm(const WideGemmArgs& a, int sm_count, cudaStream_t st) {
-  constexpr int kCS = GO2P_WD_CLUSTER;
-  const size_t smem = (size_t)kWdStages * (kWdATileBytes + NT * kWdChunkK * 2) + 256;
-  auto kernel = wide_gemm_kernel<NT, kFp16, kCS>;
+  constexpr int kCS = GO2P_WD_CLUSTER == 3 ? 2 : GO2P_WD_CLUSTER;      // 3 = CTA pair (cta_group::2)
+  constexpr bool kPair = GO2P_WD_CLUSTER == 3;
+  const size_t smem = (size_t)wd_stages(NT, kPair) * (kWdATileBytes + (kPair ? NT / 2 : NT) * kWdChunkK * 2) + 256;
+  auto kernel = wide_gemm_kernel<NT, kFp16, kCS, kPair>;
   static thread_local int configured_dev = -1;           // the attribute is per device and per function
   static thread_local int max_clusters = 0;
   int dev = 0;
@@ -383,6 +425,7 @@ inline cudaError_t wd_launch_gemm(const WideGemmArgs& a, int sm_count, cudaStrea
       e = cudaOccupancyMaxActiveClusters(&n, kernel, &cfg);   // clusters that can be co-resident (GPC boundaries)
       if (e != cudaSuccess) return e;
       if (n > 0 && n < max_clusters) max_clusters = n;
+      if (std::getenv("GO2P_DEBUG")) fprintf(stderr, "wide_gemm<%d>: %d co-resident clusters of %d (of %d SMs)\n", NT, n, kCS, sm_count);
     }
     configured_dev = dev;
   }
