@@ -80,6 +80,30 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def synthetic_raw_states(capi, n, seed):
+    """Closed-loop raw-state distribution of SURVEY.md 8(d) (small-angle attitude, joints around the default pose,
+    uniform joystick, rare dead-man press) as an array of go2p_raw_state -- bench input only, generated here so the
+    timed paths never touch oracle/."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    q0 = np.array([0.1, -0.1, 0.1, -0.1, 0.8, 0.8, 1.0, 1.0, -1.5, -1.5, -1.5, -1.5], np.float32)   # controller.hpp:119-120
+    arr = (capi.RawState * n)()
+    for i in range(n):
+        axis = rng.standard_normal(3)
+        axis /= np.linalg.norm(axis) + 1e-12
+        ang = rng.normal(0.0, 0.2)
+        r = arr[i]
+        r.quat[:] = [float(np.cos(ang / 2))] + [float(v) for v in np.sin(ang / 2) * axis]
+        r.gyro[:] = [float(v) for v in rng.normal(0, 0.5, 3)]
+        r.q[:] = [float(v) for v in q0 + rng.normal(0, 0.3, 12)]
+        r.dq[:] = [float(v) for v in rng.normal(0, 2.0, 12)]
+        r.foot_force[:] = [int(v) for v in rng.integers(0, 61, 4)]
+        r.axes[:] = [float(v) for v in rng.uniform(-1, 1, 4)]
+        r.joy_valid = 1
+        r.button0 = int(rng.random() < 0.01)
+    return arr
+
+
 def cpu_reference_rate(rows_per_step, steps, warmup, threads=None):
     """The reference path on host cores: B independent batch-1 forwards (the static-batch model's semantics,
     onnx_actor.cpp:38-48) + A9 clamp/mask, rows split over all cores -- C port in oracle/ (test infrastructure)."""
@@ -277,11 +301,8 @@ def main():
     if rank == 0 and world == 1:
         # the whole publish() for `rows` robots (raw state -> history -> policy -> clamp/mask -> q_des),
         # two launches per step, per-robot state resident in HBM (go2p_step_batch)
-        from oracle import oracle as _o
-        import __graft_entry__ as ge
         import ctypes as C
-        base = [ge.coracle_to_capi(r, capi) for r in _o.make_raw_states(4096, seed=3)]
-        arr = (capi.RawState * 4096)(*base)
+        arr = synthetic_raw_states(capi, 4096, seed=3)
         raw_np = np.frombuffer(bytes(arr), np.uint8).reshape(4096, C.sizeof(capi.RawState))
         d_raw = torch.from_numpy(np.tile(raw_np, (rows // 4096 + 1, 1))[:rows].copy()).to("cuda")
         s_obs = torch.zeros((rows, 98), device="cuda"); s_vel = torch.zeros((rows, 3), device="cuda")
@@ -304,9 +325,7 @@ def main():
         del d_raw, s_obs, s_vel, s_act, s_q
     if rank == 0 and world == 1 and not args.no_b1:
         # BASELINE.json configs[1]: batch-1 closed loop, fused pre/post, resident kernel
-        from oracle import oracle as _o
-        import __graft_entry__ as ge
-        raws = [ge.coracle_to_capi(r, capi) for r in _o.make_raw_states(512, seed=2)]
+        raws = list(synthetic_raw_states(capi, 512, seed=2))
         ctl = pkg.Go2Controller(pkg.DEFAULT_MODEL, device=local_rank)
         ctl.closed_loop(raws, 10_000)
         host_ns, dev_ns, _ = ctl.closed_loop(raws, args.b1_steps)

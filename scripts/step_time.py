@@ -4,12 +4,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import go2_onnx_controller_b200 as pkg
 from go2_onnx_controller_b200 import capi
-from oracle import oracle as _o
-import __graft_entry__ as ge
+import bench
 rows = 1_048_576
 pb = pkg.PolicyBatch(pkg.DEFAULT_MODEL)
-base = [ge.coracle_to_capi(r, capi) for r in _o.make_raw_states(4096, seed=3)]
-arr = (capi.RawState * 4096)(*base)
+arr = bench.synthetic_raw_states(capi, 4096, seed=3)
 raw_np = np.frombuffer(bytes(arr), np.uint8).reshape(4096, C.sizeof(capi.RawState))
 d_raw = torch.from_numpy(np.tile(raw_np, (rows // 4096, 1)).copy()).cuda()
 obs = torch.zeros((rows, 98), device="cuda"); vel = torch.zeros((rows, 3), device="cuda")
