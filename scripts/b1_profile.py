@@ -4,11 +4,10 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import go2_onnx_controller_b200 as pkg
 from go2_onnx_controller_b200 import capi
-from oracle import oracle
-import __graft_entry__ as ge
+import bench
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
-raws = [ge.coracle_to_capi(r, capi) for r in oracle.make_raw_states(256, seed=2)]
+raws = list(bench.synthetic_raw_states(capi, 256, seed=2))
 ctl = pkg.Go2Controller(pkg.DEFAULT_MODEL, b1_mode=capi.B1_LAUNCH)
 for _ in range(2):
     act, ms = ctl.selfdriven(raws, steps)
