@@ -357,50 +357,100 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const TcArgs a) {
     const bool even = (a.in_dim & 1) == 0;
 
     uint32_t par_acc[2] = {0u, 0u};
+    // ---- conv(s): fp32 observation rows -> 16-bit layer-0 A operand, constant ones at K = in_dim, in_dim+1.
+    //      chunk c8 (16 K elements = 8 columns) lands at 32*(c8/2) + 8*(c8%2) of buffer phi: block cb = chunks 2cb, 2cb+1
+    auto conv_job = [&](int pair, int s) {
+      const int phi = pair & 1;
+      const long long row0 = (blockIdx.x + (long long)(pair * 2 + s) * gridDim.x) * kTcTileM;
+      const int valid = (int)min((long long)kTcTileM, a.B - row0);
+      const uint32_t a0_t = tmem_base + (uint32_t)s * kTcSlotCols + lane_addr + 128u * (uint32_t)phi;
+      ptx::mbar_wait(&obs_full[s], (uint32_t)(pair & 1));
+      TC_TRACE(0x400u | (uint32_t)s);
+      const int c8_hi = min(n8, 2 * cb + 2);
+      if (valid == kTcTileM && even) {
+        // full tile in shared memory, rows 8-byte aligned: vector loads, uniform per-pair classification
+        const float2* r2 = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(stage0 + s * stage_bytes) + (size_t)m * a.in_dim);
+#pragma unroll 1
+        for (int c8 = 2 * cb; c8 < c8_hi; ++c8) {
+          uint32_t q[8];
+          if (c8 * 16 + 16 <= a.in_dim) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float2 t = r2[c8 * 8 + j]; q[j] = kFp16 ? ptx::pack_f16_sat(t.x, t.y) : ptx::pack_bf16(t.x, t.y); }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int k = c8 * 16 + 2 * j;
+              float2 t = make_float2(0.f, 0.f);
+              if (k < a.in_dim) t = r2[k >> 1]; else if (k == a.in_dim) t = make_float2(1.f, 1.f);
+              q[j] = kFp16 ? ptx::pack_f16_sat(t.x, t.y) : ptx::pack_bf16(t.x, t.y);
+            }
+          }
+          ptx::tmem_st_x8(a0_t + (uint32_t)(32 * (c8 >> 1) + 8 * (c8 & 1)), q);
+        }
+      } else {
+        const float* rowp = (valid == kTcTileM) ? reinterpret_cast<const float*>(stage0 + s * stage_bytes) + (size_t)m * a.in_dim
+                                                : a.obs + (row0 + m) * a.in_dim;
+        tc_conv_slow<kFp16>(a, rowp, m < valid, 2 * cb, c8_hi, a0_t);
+      }
+      ptx::tc_wait_st();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&a_blk[s * kTcBlocks + cb]);
+      TC_TRACE(0x500u | (uint32_t)s);
+    };
+
+    // ---- out(s) (bias already inside the accumulator): (+ELU) (+clamp/mask) (+q_des) -> global
+    auto out_job = [&](int pair, int s) {
+      const int phi = pair & 1;
+      const long long row0 = (blockIdx.x + (long long)(pair * 2 + s) * gridDim.x) * kTcTileM;
+      const int valid = (int)min((long long)kTcTileM, a.B - row0);
+      const uint32_t o_t = tmem_base + (uint32_t)s * kTcSlotCols + lane_addr + 128u * (uint32_t)((phi + 1 + L) & 1);
+      ptx::mbar_wait(&acc_full[s], par_acc[s]);
+      par_acc[s] ^= 1u;
+      ptx::tc_fence_after();
+      TC_TRACE(0x800u | (uint32_t)s);
+      if (out12 && !a.has_elu[L]) {
+        // the policy's case: 12 outputs, no activation -- column block cb < 3 stores one float4 of every row
+        if (cb < 3) {
+          uint32_t v[4];
+          ptx::tmem_ld_x4(o_t + (uint32_t)(cb * 4), v);
+          ptx::tc_wait_ld();
+          if (m < valid) {
+            const long long row = row0 + m;
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = __uint_as_float(v[j]);
+            if (a.flags & 1u) {
+              const int b0 = a.button0 ? a.button0[row] : 0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) o[j] = clamp_mask(o[j], a.action_limit, b0);
+            }
+            reinterpret_cast<float4*>(a.act + row * 12)[cb] = make_float4(o[0], o[1], o[2], o[3]);
+            if ((a.flags & 2u) && a.qdes) {
+              double2* q2 = reinterpret_cast<double2*>(a.qdes + row * kDof + cb * 4);
+              q2[0] = make_double2(joint_target(o[0], a.q0[cb * 4 + 0], a.action_scale), joint_target(o[1], a.q0[cb * 4 + 1], a.action_scale));
+              q2[1] = make_double2(joint_target(o[2], a.q0[cb * 4 + 2], a.action_scale), joint_target(o[3], a.q0[cb * 4 + 3], a.action_scale));
+            }
+          }
+        }
+      } else if (cb == 0) {
+        tc_out_generic(a, o_t, row0 + m, m < valid);
+      }
+      ptx::tc_fence_before();
+      TC_TRACE(0x900u | (uint32_t)s);
+    };
+
+    // Job order: conv(s0) conv(s1) of the first pair, then per pair  E(l,s0) E(l,s1) for every hidden layer |
+    // out(s0) conv'(s0) out(s1) conv'(s1)  where conv' converts the NEXT pair's tile of that slot.  Interleaving the
+    // output and conversion jobs of the two slots gives the output-layer MMA of slot 1 and the layer-0 MMA of slot 0
+    // a whole job of cover each (they used to be waited for).  Hazards: conv'(s) writes the buffer that held A(L),
+    // consumed by the MMA out(s) has just waited for; the layer-0 MMA of the new tile overwrites the buffer out(s)
+    // reads, but it is issued only after ALL warps signalled conv'(s), i.e. after their out(s) reads.
+    for (int s = 0; s < min(2, n_local); ++s) conv_job(0, s);
     for (int pair = 0; pair * 2 < n_local; ++pair) {
       const int ns = min(2, n_local - pair * 2);
+      const int ns_next = max(0, min(2, n_local - (pair + 1) * 2));
       const int phi = pair & 1;
-
-      // ---- conv(s): fp32 observation rows -> 16-bit layer-0 A operand, constant ones at K = in_dim, in_dim+1.
-      //      chunk c8 (16 K elements = 8 columns) lands at 32*(c8/2) + 8*(c8%2) of buffer phi: block cb = chunks 2cb, 2cb+1
-      for (int s = 0; s < ns; ++s) {
-        const long long row0 = (blockIdx.x + (long long)(pair * 2 + s) * gridDim.x) * kTcTileM;
-        const int valid = (int)min((long long)kTcTileM, a.B - row0);
-        const uint32_t a0_t = tmem_base + (uint32_t)s * kTcSlotCols + lane_addr + 128u * (uint32_t)phi;
-        ptx::mbar_wait(&obs_full[s], (uint32_t)(pair & 1));
-        TC_TRACE(0x400u | (uint32_t)s);
-        const int c8_hi = min(n8, 2 * cb + 2);
-        if (valid == kTcTileM && even) {
-          // full tile in shared memory, rows 8-byte aligned: vector loads, uniform per-pair classification
-          const float2* r2 = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(stage0 + s * stage_bytes) + (size_t)m * a.in_dim);
-#pragma unroll 1
-          for (int c8 = 2 * cb; c8 < c8_hi; ++c8) {
-            uint32_t q[8];
-            if (c8 * 16 + 16 <= a.in_dim) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) { const float2 t = r2[c8 * 8 + j]; q[j] = kFp16 ? ptx::pack_f16_sat(t.x, t.y) : ptx::pack_bf16(t.x, t.y); }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int k = c8 * 16 + 2 * j;
-                float2 t = make_float2(0.f, 0.f);
-                if (k < a.in_dim) t = r2[k >> 1]; else if (k == a.in_dim) t = make_float2(1.f, 1.f);
-                q[j] = kFp16 ? ptx::pack_f16_sat(t.x, t.y) : ptx::pack_bf16(t.x, t.y);
-              }
-            }
-            ptx::tmem_st_x8(a0_t + (uint32_t)(32 * (c8 >> 1) + 8 * (c8 & 1)), q);
-          }
-        } else {
-          const float* rowp = (valid == kTcTileM) ? reinterpret_cast<const float*>(stage0 + s * stage_bytes) + (size_t)m * a.in_dim
-                                                  : a.obs + (row0 + m) * a.in_dim;
-          tc_conv_slow<kFp16>(a, rowp, m < valid, 2 * cb, c8_hi, a0_t);
-        }
-        ptx::tc_wait_st();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&a_blk[s * kTcBlocks + cb]);
-        TC_TRACE(0x500u | (uint32_t)s);
-      }
 
       // ---- E(l,s): accumulator block -> ELU -> 16-bit A operand of the next layer, in place
       for (int l = 0; l < L; ++l) {
@@ -441,52 +491,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const TcArgs a) {
         }
       }
 
-      // ---- out(s) (bias already inside the accumulator): (+ELU) (+clamp/mask) (+q_des) -> global
       for (int s = 0; s < ns; ++s) {
-        const long long row0 = (blockIdx.x + (long long)(pair * 2 + s) * gridDim.x) * kTcTileM;
-        const int valid = (int)min((long long)kTcTileM, a.B - row0);
-        const uint32_t o_t = tmem_base + (uint32_t)s * kTcSlotCols + lane_addr + 128u * (uint32_t)((phi + 1 + L) & 1);
-        ptx::mbar_wait(&acc_full[s], par_acc[s]);
-        par_acc[s] ^= 1u;
-        ptx::tc_fence_after();
-        TC_TRACE(0x800u | (uint32_t)s);
-        if (out12 && !a.has_elu[L]) {
-          // the policy's case: 12 outputs, no activation -- column block cb < 3 stores one float4 of every row
-          if (cb < 3) {
-            uint32_t v[4];
-            ptx::tmem_ld_x4(o_t + (uint32_t)(cb * 4), v);
-            ptx::tc_wait_ld();
-            if (m < valid) {
-              const long long row = row0 + m;
-              float o[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) o[j] = __uint_as_float(v[j]);
-              if (a.flags & 1u) {
-                const int b0 = a.button0 ? a.button0[row] : 0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) o[j] = clamp_mask(o[j], a.action_limit, b0);
-              }
-              reinterpret_cast<float4*>(a.act + row * 12)[cb] = make_float4(o[0], o[1], o[2], o[3]);
-              if ((a.flags & 2u) && a.qdes) {
-                double2* q2 = reinterpret_cast<double2*>(a.qdes + row * kDof + cb * 4);
-                q2[0] = make_double2(joint_target(o[0], a.q0[cb * 4 + 0], a.action_scale), joint_target(o[1], a.q0[cb * 4 + 1], a.action_scale));
-                q2[1] = make_double2(joint_target(o[2], a.q0[cb * 4 + 2], a.action_scale), joint_target(o[3], a.q0[cb * 4 + 3], a.action_scale));
-              }
-            }
-          }
-        } else if (cb == 0) {
-          tc_out_generic(a, o_t, row0 + m, m < valid);
+        out_job(pair, s);
+        // With an even number of hidden layers the output accumulator shares its TMEM buffer with the next tile's
+        // layer-0 operand: the four warps of a lane quarter (the only ones touching these lanes) meet before any of
+        // them converts the next tile, so no conversion store can overtake a sibling's output read.  (Odd counts --
+        // the Go2 policy -- use the other buffer and skip this.)
+        if ((L & 1) == 0) {
+          __syncwarp();
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
         }
-        ptx::tc_fence_before();
-        TC_TRACE(0x900u | (uint32_t)s);
-      }
-      // With an even number of hidden layers the output accumulator shares its TMEM buffer with the next tile's
-      // layer-0 operand: the four warps of a lane quarter (the only ones touching these lanes) meet before any of them
-      // converts the next tile, so no conversion store can overtake a sibling's output read.  (Odd counts -- the Go2
-      // policy -- use the other buffer and skip this.)
-      if ((L & 1) == 0) {
-        __syncwarp();
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
+        if (s < ns_next) conv_job(pair + 1, s);
       }
     }
   }
