@@ -23,6 +23,7 @@
 #include "kernels_b1.cuh"
 #include "kernels_fp32.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_tc32.cuh"
 #include "kernels_wide.cuh"
 #include "onnx_reader.hpp"
 
@@ -426,14 +427,18 @@ int launch_fp32(go2p_handle* h, const float* d_obs, const int32_t* d_button0, fl
 template <bool kFp16>
 int launch_tc_t(go2p_handle* h, const TcArgs& a, cudaStream_t st) {
   const size_t smem = tc_smem_bytes(a);
+#ifndef GO2P_TC32
+#define GO2P_TC32 0      // 0: 18-warp kernel with control warps (kernels_tc.cuh); 1: 32-warp experiment (kernels_tc32.cuh, slower)
+#endif
+  auto kernel = GO2P_TC32 ? tc_mlp32_kernel<kFp16> : tc_mlp_kernel<kFp16>;
   static thread_local size_t set_for = 0;
   if (set_for != smem) {
-    CU_TRY(cudaFuncSetAttribute(tc_mlp_kernel<kFp16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     set_for = smem;
   }
   const long long tiles = (a.B + kTcTileM - 1) / kTcTileM;
   int grid = (int)std::min<long long>(tiles, h->sm_count - (h->resident ? 1 : 0));
-  tc_mlp_kernel<kFp16><<<grid, kTcThreads, smem, st>>>(a);
+  kernel<<<grid, GO2P_TC32 ? kTc32Threads : kTcThreads, smem, st>>>(a);
   h->last_launches++;
   CU_TRY(cudaGetLastError());
   return GO2P_OK;

@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("GO2P_LIB", os.path.join(ROOT, "go2_onnx_controller_b200", "lib", "libgo2policy_trace.so"))
 import numpy as np, torch
-trace = torch.zeros(20 * 2048, dtype=torch.int64, device="cuda")
+trace = torch.zeros(34 * 2048, dtype=torch.int64, device="cuda")
 os.environ["GO2P_TC_TRACE_PTR"] = str(trace.data_ptr())
 import go2_onnx_controller_b200 as pkg
 from go2_onnx_controller_b200 import capi
@@ -16,9 +16,9 @@ for _ in range(3):
     torch.cuda.synchronize()
     pb.infer_device(d_obs.data_ptr(), d_act.data_ptr(), B, capi.PREC_FP16)
     torch.cuda.synchronize()
-t = trace.cpu().numpy().reshape(20, 2048)
+t = trace.cpu().numpy().reshape(34, 2048)
 evs, cks = [], []
-for w in range(20):
+for w in range(34):
     n = int(t[w, 2046])
     evs.append(t[w, 0:2 * n:2]); cks.append(t[w, 1:2 * n:2])
 np.save(os.path.join(ROOT, "gpurun_out", "tc_trace_raw.npy"), t)
