@@ -205,10 +205,12 @@ int upload_model(go2p_handle* h) {
   h->cc.foot_threshold = h->cfg.foot_threshold;
   h->cc.H = h->cfg.history;
 
-  // ---- tensor-core packing (narrow family: every hidden width 128, in + 2 <= 144, out <= 16).  The chain runs
+  // ---- tensor-core packing (narrow family: every hidden width 128, in + 2 <= 128, out <= 16: the layer-0 operand
+  // with its two constant-one columns has to fit the 64 packed columns of a TMEM buffer; wider inputs take the
+  // per-layer GEMM path).  The chain runs
   // in the base-2 exponent domain (kernels_tc.cuh): an ELU layer's pre-activation and output are scaled by log2(e),
   // the next layer's weights carry the inverse factor; biases ride in two extra K rows (hi/lo).
-  bool narrow = dm.n_layers >= 2 && dm.in_dim + 2 <= kTcHidden + kTcBiasK && dm.out_dim <= kTcOutPad;
+  bool narrow = dm.n_layers >= 2 && dm.in_dim + 2 <= kTcHidden && dm.out_dim <= kTcOutPad;
   for (int l = 0; l + 1 < dm.n_layers; ++l) narrow = narrow && (m.layers[l].out == kTcHidden);
   if (narrow) {
     h->k0p = round_up(dm.in_dim + 2, 16);

@@ -446,6 +446,8 @@ def test_resident_kernel_coexists_with_batched_kernels(torch_cuda, model_path, g
     dict(dims=(77, 128, 128, 7), alpha=0.5, final_act=False),        # odd input width, 3 layers, 7 outputs
     dict(dims=(64, 128, 12), alpha=1.0, final_act=True),             # 2 layers, ELU on the output layer too
     dict(dims=(40, 128, 128, 128, 128, 16), alpha=1.3, final_act=False),    # 5 layers, widest output the TC kernel serves
+    dict(dims=(126, 128, 128, 12), alpha=1.0, final_act=False),      # widest input of the one-kernel path (126 + 2 ones = 128)
+    dict(dims=(140, 128, 128, 12), alpha=1.0, final_act=False),      # wider input: served by the per-layer GEMM kernels
 ])
 def test_other_narrow_policies_all_paths(torch_cuda, tmp_path, shape):
     """The kernels are driven by the parsed graph, not by the bundled policy's constants: other layer counts, input
