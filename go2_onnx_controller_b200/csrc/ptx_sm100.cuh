@@ -55,27 +55,22 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-// A protocol bug must surface as a launch failure, never as a hung GPU: a wait that lasts more than
-// 4 s of wall clock traps (checked every 4096 failed polls, so the fast path never reads the timer).
-__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  uint64_t t0 = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0xFFFu) == 0) {
-      uint64_t now;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ull) __trap();
-    }
-  }
-}
+// A protocol bug must surface as a launch failure, never as a hung GPU: the wait traps after 2^25 failed polls.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  // fast path inline: a short rolled retry loop (every failed try_wait already sleeps in hardware, so a handful of
-  // retries covers every wait of a healthy pipeline); the watchdog loop lives out of line to keep hot code small
-#pragma unroll 1
-  for (int i = 0; i < 32; ++i)
-    if (mbar_try_wait(bar, parity)) return;
-  mbar_wait_slow(bar, parity);
+  // the whole wait as one PTX loop: two instructions when the phase is already complete, no convergence bookkeeping;
+  // the watchdog is a poll counter (a failed try_wait parks the warp for a bounded time, so 2^25 polls is seconds)
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .pred q;\n\t.reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n"
+      "GO2P_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra GO2P_DONE;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 q, n, 0x2000000;\n\t"
+      "@q bra GO2P_WAIT;\n\t"
+      "trap;\n"
+      "GO2P_DONE:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
 // generic-proxy smem writes -> visible to the async proxy (tensor core / TMA reads)
