@@ -267,12 +267,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const TcArgs a) {
 
   if (warp >= kTcCtrlWarp0) {
     // ================= control warp of slot s: bulk-copy producer + MMA issuer =================
-    // One warp per slot walks that slot's tiles and layers and blocks on the A-ready barrier of each 32-column
-    // block in the fixed order 0,1,2,3, issuing that block's K steps at once:
-    // the MMA trails the epilogue, and the fixed order keeps the fp32 accumulation order (every output bit)
-    // independent of timing.  Layer 0 waits for all four blocks (its first K step overwrites the buffer the
-    // previous tile's output epilogue reads, and a warp signals its blocks only after that read); at that point
-    // the observation stage of this slot is free as well, so the next tile's bulk copy is issued right there.
+    // One warp per slot walks that slot's tiles and layers: it waits for the A-ready barriers of the four 32-column
+    // blocks and issues the layer's K steps back to back in a fixed order, which keeps the fp32 accumulation order
+    // (every output bit) independent of timing.  Layer 0's first K step overwrites the buffer the previous tile's
+    // output epilogue reads -- safe, because a warp signals its conversion block only after that read; at that
+    // point the observation stage of this slot is free as well, so the next tile's bulk copy is issued right there.
     const int s = warp - kTcCtrlWarp0;
     const uint32_t fmt = kFp16 ? ptx::FMT_F16 : ptx::FMT_BF16;
     const uint32_t w_base = ptx::smem_u32(w_smem);
@@ -343,9 +342,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const TcArgs a) {
   } else {
     // ================= worker warps: one pool of 16 warps walks the job list of both slots =================
     // pool = 4 TMEM lane quarters x 4 column blocks (warp = cb*4 + quarter): every warp owns one 32-column block.
-    // Job order per pair of tiles: conv(s0) conv(s1) | E(l,s0) E(l,s1) for every hidden layer | out(s0) out(s1).
-    // While the pool works on one slot, the other slot's next-layer MMA (which trailed its epilogue block by block)
-    // completes, so the pool never waits for a hand-off in steady state and the MUFU pipe has 4 warps per scheduler.
+    // Job order: see below (E jobs alternate between the slots, output and conversion jobs are interleaved).
+    // While the pool works on one slot, the other slot's next-layer MMAs are issued and complete.
     const int quarter = warp & 3;            // TMEM lane quarter this warp may touch (== warp % 4)
     const int cb = warp >> 2;                // 32-column block
     const uint32_t lane_addr = ((uint32_t)(quarter * 32)) << 16;
