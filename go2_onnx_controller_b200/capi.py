@@ -64,6 +64,7 @@ _fp = C.POINTER(C.c_float)
 SIGNATURES = {
     "go2p_config_default": (None, [C.POINTER(Config)]),
     "go2p_create": (C.c_int, [C.c_char_p, C.POINTER(Config), C.POINTER(_H)]),
+    "go2p_inspect_model": (C.c_int, [C.c_char_p, C.POINTER(ModelInfo), C.POINTER(C.c_double)]),
     "go2p_destroy": (C.c_int, [_H]),
     "go2p_model_info": (C.c_int, [_H, C.POINTER(ModelInfo)]),
     "go2p_last_error": (C.c_char_p, []),

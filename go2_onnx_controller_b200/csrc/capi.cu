@@ -620,6 +620,38 @@ int go2p_model_info(const go2p_handle* h, go2p_model_info_t* info) {
   return GO2P_OK;
 }
 
+int go2p_inspect_model(const char* onnx_path, go2p_model_info_t* info, double* checksum) {
+  if (!onnx_path || !info) return fail(GO2P_ERR_INVALID, "go2p_inspect_model: null argument");
+  static thread_local MlpModel model;
+  try {
+    model = load_onnx_mlp(onnx_path);
+  } catch (const std::exception& e) {
+    const std::string what = e.what();
+    return fail(what.rfind("io:", 0) == 0 ? GO2P_ERR_IO : GO2P_ERR_MODEL, what);
+  }
+  if ((int)model.layers.size() > kMaxLayers) return fail(GO2P_ERR_UNSUPPORTED, "more than 8 Gemm layers");
+  std::memset(info, 0, sizeof(*info));
+  info->n_layers = (int)model.layers.size();
+  info->in_dim = model.layers.front().in;
+  info->out_dim = model.layers.back().out;
+  info->dims[0] = info->in_dim;
+  double sum = 0.0;
+  for (int l = 0; l < info->n_layers; ++l) {
+    const MlpLayer& L = model.layers[l];
+    info->dims[l + 1] = L.out;
+    info->has_elu[l] = L.has_elu ? 1 : 0;
+    info->elu_alpha[l] = L.elu_alpha;
+    size_t i = 0;
+    for (float w : L.weight) sum += (double)((i++ % 97) + 1) * (double)w;
+    for (float b : L.bias) sum += (double)((i++ % 97) + 1) * (double)b;
+  }
+  info->input_name = model.input_name.c_str();
+  info->output_name = model.output_name.c_str();
+  info->n_params = model.n_params();
+  if (checksum) *checksum = sum;
+  return GO2P_OK;
+}
+
 // ------------------------------------------------------------------------------------- batch-1
 int go2p_persistent_start(go2p_handle* h) {
   if (!h) return fail(GO2P_ERR_INVALID, "null handle");

@@ -132,6 +132,11 @@ int go2p_create(const char* onnx_path, const go2p_config* cfg, go2p_handle** out
 int go2p_destroy(go2p_handle* h);
 /* replaces session_.GetInputNameAllocated / GetInputTypeInfo ..., onnx_actor.cpp:23-28 */
 int go2p_model_info(const go2p_handle* h, go2p_model_info_t* info);
+/* the same facts straight from a file, without a device (what print_model_info needs, onnx_actor.cpp:60-66):
+ * parses the graph, fills dims / activations / names (strings owned by the library, valid until the calling
+ * thread's next go2p_inspect_model) and, if checksum != NULL, a positional checksum of every layer's
+ * [out][in] weights and bias: sum over elements of ((i mod 97) + 1) * value in double, layer after layer. */
+int go2p_inspect_model(const char* onnx_path, go2p_model_info_t* info, double* checksum);
 const char* go2p_last_error(void);
 int go2p_abi_version(void);
 

@@ -105,6 +105,56 @@ def test_other_spellings_of_linear_layers_parse(lib, tmp_path, form, tail):
     assert rc == capi.ERR_MODEL and msg
 
 
+def _checksum(policy):
+    tot = 0.0
+    for l in policy.layers:
+        v = np.concatenate([l.weight.ravel(), l.bias.ravel()]).astype(np.float64)
+        tot += float(((np.arange(v.size) % 97) + 1) @ v)
+    return tot
+
+
+def test_inspect_bundled_model_without_device(lib, model_path):
+    """What print_model_info reports (reference: onnx_actor.cpp:60-66), parsed by the C++ reader with no GPU, and
+    a positional checksum of every weight against the oracle-side reader of the same file."""
+    info, cs = capi.ModelInfo(), C.c_double()
+    assert lib.go2p_inspect_model(os.fspath(model_path).encode(), C.byref(info), C.byref(cs)) == capi.OK
+    assert [info.dims[i] for i in range(info.n_layers + 1)] == [98, 128, 128, 128, 12]
+    assert [info.has_elu[i] for i in range(4)] == [1, 1, 1, 0] and info.elu_alpha[0] == 1.0
+    assert info.input_name == b"observation" and info.output_name == b"action" and info.n_params == 47244
+    pol = onnx_mini.load_policy(os.fspath(model_path))
+    assert abs(cs.value - _checksum(pol)) <= 1e-9 * max(1.0, abs(cs.value))
+
+
+@pytest.mark.parametrize("kw", [
+    dict(trans_b=False), dict(packed_dims=True), dict(use_float_data=True), dict(batch="batch"),
+    dict(form="matmul_add"), dict(form="mixed", identity_tail=True), dict(final_activation=True),
+])
+def test_reader_agrees_with_oracle_reader_on_every_spelling(lib, tmp_path, kw):
+    """Every serialisation variant the writer can produce parses to the same layers in the C++ reader (product) and
+    the Python reader (oracle): dims, activations, alpha and the positional weight checksum."""
+    rng = np.random.default_rng(len(str(kw)))
+    dims = (23, 40, 17, 9)
+    ws = [rng.normal(0, 1, (n, k)).astype(np.float32) for k, n in zip(dims[:-1], dims[1:])]
+    bs = [rng.normal(0, 1, n).astype(np.float32) for n in dims[1:]]
+    p = tmp_path / "m.onnx"
+    p.write_bytes(onnx_mini.write_mlp_onnx(ws, bs, 0.7, **kw))
+    info, cs = capi.ModelInfo(), C.c_double()
+    rc = lib.go2p_inspect_model(os.fspath(p).encode(), C.byref(info), C.byref(cs))
+    assert rc == capi.OK, lib.go2p_last_error().decode()
+    pol = onnx_mini.load_policy(os.fspath(p))
+    assert [info.dims[i] for i in range(info.n_layers + 1)] == list(dims)
+    assert [bool(info.has_elu[i]) for i in range(3)] == [l.elu_alpha is not None for l in pol.layers]
+    assert all(abs(info.elu_alpha[i] - 0.7) < 1e-7 for i in range(3) if info.has_elu[i])
+    assert abs(cs.value - _checksum(pol)) <= 1e-9 * max(1.0, abs(cs.value))
+    assert all(np.array_equal(l.weight, w) and np.array_equal(l.bias, b) for l, w, b in zip(pol.layers, ws, bs))
+
+
+def test_inspect_errors(lib, tmp_path):
+    info = capi.ModelInfo()
+    assert lib.go2p_inspect_model(os.fspath(tmp_path / "nope.onnx").encode(), C.byref(info), None) == capi.ERR_IO
+    assert lib.go2p_inspect_model(None, C.byref(info), None) == capi.ERR_INVALID
+
+
 def test_struct_size_mismatch_is_invalid(lib, model_path):
     cfg = actor.default_config()
     cfg.struct_size = 8
