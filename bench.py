@@ -338,6 +338,15 @@ def main():
         r0, _, thr = cpu_reference_rate(32768, 1, 1)
         passes = int(max(1, min(64, round(r0 * 12 / rows))))          # ~12 s of CPU work over the same rows
         rate, dtc, thr = cpu_reference_rate(rows, passes, 0)
+        # the control-loop step on one host core (C restatement of publish(), fp32 forward)
+        from oracle import coracle
+        cm1 = coracle.CModel(pkg.DEFAULT_MODEL)
+        raws1 = [coracle.RawState.from_buffer_copy(bytes(r)) for r in synthetic_raw_states(capi, 512, seed=2)]
+        coracle.closed_loop_latency_ns(cm1, raws1, 10_000)
+        ns1 = coracle.closed_loop_latency_ns(cm1, raws1, 100_000)
+        line["b1_cpu_port_us"] = {"steps": 100_000, "p50": float(np.percentile(ns1, 50)) / 1e3, "p99": float(np.percentile(ns1, 99)) / 1e3,
+                                  "cores": 1, "kind": "port",
+                                  "note": "C restatement of publish() (A1-A11, fp32 forward) on one host thread; ONNX Runtime itself is not installable here"}
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": thr, "kind": "port",
                                 "sample": f"{passes} passes over {rows} rows of the same N(0,1) workload in {dtc:.1f} s; C restatement "
                                           "(oracle/oracle_mlp.c), batch-1 semantics per row, OpenMP over all host cores; "

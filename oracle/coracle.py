@@ -64,8 +64,8 @@ class StepOut(C.Structure):
 
 def build(force: bool = False) -> None:
     """Compile the C restatement and, where the reference tree is present, oracle/_ref."""
-    if force or not os.path.exists(LIB_PATH):
-        subprocess.run(["make", "-C", HERE, LIB_PATH], check=True, capture_output=True)
+    # make is incremental: always ask it, so an edited source never meets a stale library
+    subprocess.run(["make", "-C", HERE, LIB_PATH] + (["-B"] if force else []), check=True, capture_output=True)
     subprocess.run(["make", "-C", HERE, "ref"], check=False, capture_output=True)
 
 
@@ -92,6 +92,9 @@ def lib():
         L.orc_ctrl_assemble.argtypes = [C.POINTER(CtrlState), C.POINTER(RawState), fp]
         L.orc_ctrl_post.argtypes = [C.POINTER(CtrlState), C.POINTER(RawState), fp, C.POINTER(StepOut)]
         L.orc_ctrl_step.argtypes = [C.POINTER(CtrlState), C.POINTER(OrcModel), C.POINTER(RawState), C.c_int, C.POINTER(StepOut)]
+        L.orc_ctrl_closed_loop_ns.argtypes = [C.POINTER(OrcModel), C.c_int, C.POINTER(RawState), C.c_int, C.c_int64,
+                                              C.POINTER(C.c_uint64)]
+        L.orc_ctrl_closed_loop_ns.restype = C.c_float
         _lib = L
     return _lib
 
@@ -136,6 +139,14 @@ class CModel:
         Y = np.empty((X.shape[0], self.out_dim), np.float64)
         lib().orc_forward_rows_f64(self._p, _fp(X), _dp(Y), X.shape[0], threads)
         return Y
+
+
+def closed_loop_latency_ns(model: "CModel", raws, steps: int, H: int = 2) -> np.ndarray:
+    """Per-step wall time (ns) of the restated publish() on ONE host thread, fp32 forward."""
+    arr = (RawState * len(raws))(*raws)
+    out = np.zeros(steps, np.uint64)
+    lib().orc_ctrl_closed_loop_ns(model._p, H, arr, len(raws), steps, out.ctypes.data_as(C.POINTER(C.c_uint64)))
+    return out
 
 
 def raw_from_py(r) -> RawState:

@@ -92,6 +92,10 @@ void orc_ctrl_assemble(orc_ctrl_state* s, const orc_raw_state* raw, float* obs);
 void orc_ctrl_post(orc_ctrl_state* s, const orc_raw_state* raw, const float* action_raw, orc_step_out* out);
 /* full step with the oracle's own forward: use_f64 selects fp64 or fp32 arithmetic for A7 */
 void orc_ctrl_step(orc_ctrl_state* s, const orc_model* m, const orc_raw_state* raw, int use_f64, orc_step_out* out);
+/* closed loop on one host thread, fp32 forward: `steps` publish() steps over the raw states (cycled), each timed
+ * with CLOCK_MONOTONIC; ns_out[steps].  The CPU stand-in for the reference's control-loop step (SURVEY 8d config 1:
+ * ONNX Runtime itself is not available). Returns the last action's first component (keeps the loop observable). */
+float orc_ctrl_closed_loop_ns(const orc_model* m, int H, const orc_raw_state* raws, int n_raws, int64_t steps, uint64_t* ns_out);
 
 #ifdef __cplusplus
 }

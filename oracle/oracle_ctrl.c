@@ -118,3 +118,19 @@ void orc_ctrl_step(orc_ctrl_state* s, const orc_model* m, const orc_raw_state* r
   }
   orc_ctrl_post(s, raw, a, out);
 }
+
+/* reference: controller.cpp:173-251 executed `steps` times, one thread, per-step wall time */
+#include <time.h>
+float orc_ctrl_closed_loop_ns(const orc_model* m, int H, const orc_raw_state* raws, int n_raws, int64_t steps, uint64_t* ns_out) {
+  orc_ctrl_state st;
+  orc_step_out out;
+  orc_ctrl_reset(&st, H);
+  for (int64_t i = 0; i < steps; ++i) {
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    orc_ctrl_step(&st, m, &raws[i % n_raws], 0, &out);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (ns_out) ns_out[i] = (uint64_t)((t1.tv_sec - t0.tv_sec) * 1000000000ll + (t1.tv_nsec - t0.tv_nsec));
+  }
+  return out.action[0];
+}
