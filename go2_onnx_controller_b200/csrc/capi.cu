@@ -372,7 +372,9 @@ int ensure_scratch(go2p_handle* h, int64_t rows) {
   go2p_handle::Scratch& sc = h->scratch_sets[h->scratch_sel];
   if (sc.rows >= rows) return GO2P_OK;
   for (int i = 0; i < 2; ++i) {
-    if (sc.buf[i]) cudaFree(sc.buf[i]);
+    // outgrown buffers are retired, not freed: cudaFree synchronises the device and would never return while the
+    // resident batch-1 kernel runs, and kernels of other streams may still read them; go2p_destroy frees them
+    if (sc.buf[i]) h->dev_owned.push_back(sc.buf[i]);
     sc.buf[i] = nullptr;
   }
   sc.rows = 0;
@@ -936,7 +938,7 @@ int go2p_step_batch(go2p_handle* h, const go2p_raw_state* d_raw, float* d_vel_cm
   DeviceGuard g(h->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (h->step_button_rows < B) {
-    if (h->d_step_button) { CU_TRY(cudaStreamSynchronize(st)); CU_TRY(cudaFree(h->d_step_button)); h->d_step_button = nullptr; }
+    if (h->d_step_button) { h->dev_owned.push_back(h->d_step_button); h->d_step_button = nullptr; }   // retired, see ensure_scratch
     CU_TRY(cudaMalloc((void**)&h->d_step_button, (size_t)B * sizeof(int32_t)));
     h->step_button_rows = B;
   }

@@ -72,6 +72,7 @@ struct WideModel {
   static constexpr int kSets = 4;
   mutable uint16_t* act[kSets][2] = {};
   mutable long long act_rows[kSets] = {};
+  mutable std::vector<void*> retired;     // outgrown buffers: freed with the model (cudaFree would synchronise the device)
 };
 
 struct WideGemmArgs {
@@ -440,6 +441,8 @@ inline void wide_release(WideModel* wm) {
     for (int i = 0; i < 2; ++i) { if (wm->act[s][i]) cudaFree(wm->act[s][i]); wm->act[s][i] = nullptr; }
     wm->act_rows[s] = 0;
   }
+  for (void* p : wm->retired) cudaFree(p);
+  wm->retired.clear();
 }
 
 // rows per pass: 148 row tiles, so every layer's job count is a whole number of waves over the 148 SMs, and the widest
@@ -453,7 +456,7 @@ inline int wide_launch(const WideModel& wm, const float* d_obs, const int32_t* d
   const long long chunk = std::min<long long>(B, kWdChunkRows);
   const long long chunk_tiles = (chunk + kWdTileM - 1) / kWdTileM;
   if (wm.act_rows[set] < chunk_tiles * kWdTileM) {
-    for (int i = 0; i < 2; ++i) { if (act[i]) cudaFree(act[i]); act[i] = nullptr; }
+    for (int i = 0; i < 2; ++i) { if (act[i]) wm.retired.push_back(act[i]); act[i] = nullptr; }
     const size_t bytes = (size_t)chunk_tiles * kWdTileM * wm.max_kp * 2;
     if (cudaMalloc((void**)&act[0], bytes) != cudaSuccess || cudaMalloc((void**)&act[1], bytes) != cudaSuccess) {
       err = "wide_launch: cudaMalloc of the activation buffers failed"; return 4;
