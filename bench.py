@@ -104,7 +104,7 @@ def synthetic_raw_states(capi, n, seed):
     return arr
 
 
-def cpu_reference_rate(rows_per_step, steps, warmup, threads=None):
+def cpu_reference_rate(rows_per_step, steps, warmup, threads=None, blocked=False):
     """The reference path on host cores: B independent batch-1 forwards (the static-batch model's semantics,
     onnx_actor.cpp:38-48) + A9 clamp/mask, rows split over all cores -- C port in oracle/ (test infrastructure)."""
     import numpy as np
@@ -116,10 +116,10 @@ def cpu_reference_rate(rows_per_step, steps, warmup, threads=None):
     threads = threads or len(os.sched_getaffinity(0))
     X = oracle.make_obs_d1(rows_per_step, 98, seed=0)
     for _ in range(warmup):
-        cm.forward_f32(X[: max(1, rows_per_step // 8)], threads)
+        cm.forward_f32(X[: max(1, rows_per_step // 8)], threads, blocked)
     t0 = time.perf_counter()
     for _ in range(steps):
-        y = cm.forward_f32(X, threads)
+        y = cm.forward_f32(X, threads, blocked)
         oracle.clamp_mask(y, 0)
     dt = time.perf_counter() - t0
     return rows_per_step * steps / dt, dt, threads
@@ -338,6 +338,8 @@ def main():
         r0, _, thr = cpu_reference_rate(32768, 1, 1)
         passes = int(max(1, min(64, round(r0 * 12 / rows))))          # ~12 s of CPU work over the same rows
         rate, dtc, thr = cpu_reference_rate(rows, passes, 0)
+        # the "generous" CPU arm of SURVEY 8d: row-blocked forward (weights reused across rows), all cores, ~3 s
+        rate_b, dtb, _ = cpu_reference_rate(rows, max(1, passes // 4), 0, blocked=True)
         # the control-loop step on one host core (C restatement of publish(), fp32 forward)
         from oracle import coracle
         cm1 = coracle.CModel(pkg.DEFAULT_MODEL)
@@ -347,6 +349,9 @@ def main():
         line["b1_cpu_port_us"] = {"steps": 100_000, "p50": float(np.percentile(ns1, 50)) / 1e3, "p99": float(np.percentile(ns1, 99)) / 1e3,
                                   "cores": 1, "kind": "port",
                                   "note": "C restatement of publish() (A1-A11, fp32 forward) on one host thread; ONNX Runtime itself is not installable here"}
+        line["cpu_baseline_blocked"] = {"value": rate_b, "unit": UNIT, "cores": thr, "kind": "port",
+                                        "sample": f"{max(1, passes // 4)} passes over {rows} rows in {dtb:.1f} s; row-blocked C forward "
+                                                  "(oracle_mlp.c: orc_forward_blocked_f32), a batched CPU implementation the reference does not have"}
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": thr, "kind": "port",
                                 "sample": f"{passes} passes over {rows} rows of the same N(0,1) workload in {dtc:.1f} s; C restatement "
                                           "(oracle/oracle_mlp.c), batch-1 semantics per row, OpenMP over all host cores; "
