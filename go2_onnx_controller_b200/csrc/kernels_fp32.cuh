@@ -152,7 +152,7 @@ small_out_kernel(const float* __restrict__ A, int lda, const float* __restrict__
 
 // Elementwise A9/A11 for models whose output layer is too wide for small_out_kernel.
 __global__ void post_kernel(float* __restrict__ act, long long total, int out_dim, uint32_t flags,
-                            const int32_t* __restrict__ button0, double* __restrict__ qdes, CtrlConst cc) {
+                            const int32_t* __restrict__ button0, double* __restrict__ qdes, const __grid_constant__ CtrlConst cc) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const long long row = i / out_dim;

@@ -216,7 +216,7 @@ __device__ __noinline__ void tc_out_generic(const TcArgs& a, uint32_t o_t, long 
 }
 
 template <bool kFp16>
-__global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const TcArgs a) {
+__global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 

@@ -47,7 +47,7 @@ __device__ __noinline__ void tc32_conv_slow(const TcArgs& a, const float* rowp, 
 }
 
 template <bool kFp16>
-__global__ void __launch_bounds__(kTc32Threads, 1) tc_mlp32_kernel(const TcArgs a) {
+__global__ void __launch_bounds__(kTc32Threads, 1) tc_mlp32_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
