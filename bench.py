@@ -28,8 +28,9 @@ sys.path.insert(0, ROOT)
 ALGO_BYTES_PER_INF = 98 * 4 + 12 * 4          # obs in + action out, weights amortised
 ALGO_FLOP_PER_INF = 93696
 # dram__bytes_read.sum + dram__bytes_write.sum of one tc_mlp_kernel launch over 1,048,576 rows, from the ncu
-# --set full capture summarised in profiles/r01_tc_mlp_kernel_final_details.txt (416.0 MB + 63.3 MB)
-NCU_TRAFFIC_BYTES_PER_ROW = (415.985152e6 + 63.315968e6) / 1048576
+# --set full capture summarised in profiles/r01_tc_mlp_kernel_final_details.txt (415.6 MB read + 44.1 MB
+# written; part of the 50 MB of actions is still in L2 when the launch ends -- the capture before it showed 63 MB)
+NCU_TRAFFIC_BYTES_PER_ROW = (415.561984e6 + 44.075008e6) / 1048576
 METRIC = "policy_inferences_per_sec"
 UNIT = "inferences/s"
 
