@@ -198,3 +198,19 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "liboracle" not in src and "oracle/" not in src, f
+
+
+def test_bench_raw_state_generator_matches_both_struct_layouts():
+    """bench.py generates its closed-loop inputs itself (the timed paths never touch oracle/); the C-ABI struct and the
+    oracle's struct must be the same 156 bytes so the CPU leg can replay exactly the same raw states."""
+    import bench
+    from oracle import coracle
+    arr = bench.synthetic_raw_states(capi, 16, seed=7)
+    assert C.sizeof(capi.RawState) == C.sizeof(coracle.RawState) == 156
+    for r in arr:
+        o = coracle.RawState.from_buffer_copy(bytes(r))
+        assert list(o.quat) == list(r.quat) and list(o.q) == list(r.q) and list(o.foot_force) == list(r.foot_force)
+        assert o.joy_valid == r.joy_valid == 1 and o.button0 == r.button0
+        assert abs(sum(v * v for v in r.quat) - 1.0) < 1e-5 and all(0 <= f <= 60 for f in r.foot_force)
+    again = bench.synthetic_raw_states(capi, 16, seed=7)
+    assert bytes(again) == bytes(arr)            # seeded: the same inputs on every rank and every run
