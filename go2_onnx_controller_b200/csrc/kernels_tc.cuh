@@ -15,9 +15,9 @@
 //     tcgen05.ld, apply ELU, pack to 16 bit and write the result back IN PLACE (the first 16 columns of
 //     every 32-column block) with tcgen05.st, where the next layer's tcgen05.mma reads it as its A
 //     operand (TS form) while accumulating into the other buffer.  The activation never leaves the SM;
-//   * A-operand readiness is tracked per 32-column block (one mbarrier each, 4 arrivals = 4 lane quarters); the
-//     slot's control warp waits for the four blocks and issues the layer's K steps back to back in a fixed order,
-//     so the fp32 accumulation order (every output bit) does not depend on timing;
+//   * A-operand readiness is one mbarrier per slot (16 arrivals = the 16 worker warps); the slot's control warp
+//     waits for it and issues the layer's K steps back to back in a fixed order, so the fp32 accumulation order
+//     (every output bit) does not depend on timing;
 //   * the bias rides inside the MMA: every A operand carries two constant 1.0 columns and the weight
 //     matrix two extra K rows holding hi/lo halves of the bias, so the epilogue has no bias add;
 //   * the chain is evaluated in the base-2 exponent domain: layer l produces z' = log2(e)*z, the ELU is
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
   uint64_t* obs_full = bars;        // [2]
   uint64_t* obs_empty = bars + 2;   // [2]
   uint64_t* acc_full = bars + 4;    // [2]
-  uint64_t* a_blk = bars + 6;       // [2][4]  A operand of the next layer ready, per 32-column block
+  uint64_t* a_blk = bars + 6;       // [2][4], entry [s][0] used: A operand of slot s's next layer ready (16 arrivals)
   uint64_t* w_full = bars + 14;     // [kMaxLayers]  layer weights landed in shared memory (completes once)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14 + kMaxLayers);
 
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
       for (int s = 0; s < 2; ++s) {
         ptx::mbar_init(&obs_full[s], 1);
         ptx::mbar_init(&acc_full[s], 1);
-        for (int b = 0; b < kTcBlocks; ++b) ptx::mbar_init(&a_blk[s * kTcBlocks + b], 4);   // 4 lane quarters
+        ptx::mbar_init(&a_blk[s * kTcBlocks], kTcWorkers);   // one A-ready barrier per slot: every worker warp arrives once per job
       }
       for (int l = 0; l < a.n_layers; ++l) ptx::mbar_init(&w_full[l], 1);
       ptx::fence_mbar_init();
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
         const uint32_t dst = tmem_base + (uint32_t)s * kTcSlotCols + 128u * (uint32_t)((phi + l + 1) & 1);
         ptx::mbar_wait(&w_full[l], 0u);      // completes once; later waits return at the first probe
         if (l == 0) {
-          for (int q = 0; q < kTcBlocks; ++q) ptx::mbar_wait(&blk[q], par);
+          ptx::mbar_wait(&blk[0], par);
           ptx::tc_fence_after();
           if (ptx::elect_one_sync()) {
             if (i + 2 < n_local) load_tile(i + 2);
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
           // 16 pool warps finish a job within ~300 cycles of each other, so issuing block by block gained nothing and
           // cost ~120 cycles of control-warp latency per MMA (wait + fence + elect per block) against ~55 when the
           // MMAs are issued in one go -- enough to make the pool wait for the accumulator at every job.
-          for (int q = 0; q < kTcBlocks; ++q) ptx::mbar_wait(&blk[q], par);
+          ptx::mbar_wait(&blk[0], par);
           ptx::tc_fence_after();
           if (ptx::elect_one_sync()) {
             TC_TRACE(0x200u | (uint32_t)(l << 4) | (uint32_t)s);
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
       ptx::tc_wait_st();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&a_blk[s * kTcBlocks + cb]);
+      if (lane == 0) ptx::mbar_arrive(&a_blk[s * kTcBlocks]);
       TC_TRACE(0x500u | (uint32_t)s);
     };
 
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
           TC_TRACE(0xF00u | (4u << 4) | (uint32_t)s);
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&a_blk[s * kTcBlocks + cb]);
+          if (lane == 0) ptx::mbar_arrive(&a_blk[s * kTcBlocks]);
           TC_TRACE(0x700u | (uint32_t)(l << 4) | (uint32_t)s);
         }
       }
