@@ -23,7 +23,6 @@
 #include "kernels_b1.cuh"
 #include "kernels_fp32.cuh"
 #include "kernels_tc.cuh"
-#include "kernels_tc32.cuh"
 #include "kernels_wide.cuh"
 #include "onnx_reader.hpp"
 
@@ -71,6 +70,9 @@ struct go2p_handle {
   bool wide_ok = false;
   uint16_t* d_wpack[2] = {nullptr, nullptr};   // [0] bf16, [1] fp16
   int k0p = 0;
+  size_t tc_attr_smem[2] = {0, 0};             // dynamic shared memory opted in for tc_mlp_kernel<bf16|fp16> on this device
+  bool b1_attr_set = false;                    // same for the one-shot batch-1 kernel
+  size_t so_attr_smem = 0;                     // same for small_out_kernel
   WideModel wide{};
   // fp32 path scratch (activations between the per-layer launches): set 0 serves the device-pointer API,
   // sets 1..kPipeDepth the streams of the host-buffer pipeline (which run concurrently)
@@ -341,10 +343,9 @@ int b1_dispatch(go2p_handle* h) {
   }
   bool fit;
   const size_t smem = b1_smem_bytes(h, false, &fit);
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
+  if (!h->b1_attr_set) {
     CU_TRY(cudaFuncSetAttribute(b1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    h->b1_attr_set = true;
   }
   B1Args a = make_b1_args(h, false);
   b1_kernel<false><<<1, kB1Threads, smem, h->b1_stream>>>(a);
@@ -431,18 +432,15 @@ int launch_fp32(go2p_handle* h, const float* d_obs, const int32_t* d_button0, fl
 template <bool kFp16>
 int launch_tc_t(go2p_handle* h, const TcArgs& a, cudaStream_t st) {
   const size_t smem = tc_smem_bytes(a);
-#ifndef GO2P_TC32
-#define GO2P_TC32 0      // 0: 18-warp kernel with control warps (kernels_tc.cuh); 1: 32-warp experiment (kernels_tc32.cuh, slower)
-#endif
-  auto kernel = GO2P_TC32 ? tc_mlp32_kernel<kFp16> : tc_mlp_kernel<kFp16>;
-  static thread_local size_t set_for = 0;
-  if (set_for != smem) {
+  auto kernel = tc_mlp_kernel<kFp16>;
+  // the opt-in is a per-device function attribute: remembered per handle (one handle = one device)
+  if (h->tc_attr_smem[kFp16 ? 1 : 0] != smem) {
     CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    set_for = smem;
+    h->tc_attr_smem[kFp16 ? 1 : 0] = smem;
   }
   const long long tiles = (a.B + kTcTileM - 1) / kTcTileM;
   int grid = (int)std::min<long long>(tiles, h->sm_count - (h->resident ? 1 : 0));
-  kernel<<<grid, GO2P_TC32 ? kTc32Threads : kTcThreads, smem, st>>>(a);
+  kernel<<<grid, kTcThreads, smem, st>>>(a);
   h->last_launches++;
   CU_TRY(cudaGetLastError());
   return GO2P_OK;

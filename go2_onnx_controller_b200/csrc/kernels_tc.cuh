@@ -32,13 +32,6 @@
 #include "policy_dev.cuh"
 #include "ptx_sm100.cuh"
 
-#ifndef GO2P_TC_POLY_PAIRS
-#define GO2P_TC_POLY_PAIRS 1
-#endif
-#ifndef GO2P_TC_HALF_ELU
-#define GO2P_TC_HALF_ELU 1
-#endif
-
 namespace go2p {
 
 constexpr int kTcTileM = 128;
@@ -97,77 +90,60 @@ __host__ __device__ inline size_t tc_weight_bytes(const TcArgs& a) {
 __host__ __device__ inline size_t tc_stage_bytes(const TcArgs& a) { return ((size_t)kTcTileM * a.in_dim * 4 + 127) & ~(size_t)127; }
 __host__ __device__ inline size_t tc_smem_bytes(const TcArgs& a) { return tc_weight_bytes(a) + 2 * tc_stage_bytes(a) + 256; }
 
-// ELU in the base-2 domain on 32 accumulator columns -> 16 words of packed 16-bit operands.
-//   e = 2^z' (MUFU), f = c*e - c (FFMA), result = z' < 0 ? f : z' selected on the packed pair.
-// same on 8 accumulator columns -> 4 packed words (the rolled epilogue loop works in groups of 8 columns)
-template <bool kFp16>
-__device__ __forceinline__ void elu_pack8(const uint32_t (&v)[8], bool has_elu, float c, uint32_t (&p)[4]) {
-  const float nc = -c;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float z0 = __uint_as_float(v[2 * j]), z1 = __uint_as_float(v[2 * j + 1]);
-    const uint32_t zp = kFp16 ? ptx::pack_f16_sat(z0, z1) : ptx::pack_bf16(z0, z1);
-    if (has_elu) {
-      const float f0 = fmaf(ptx::ex2_approx(z0), c, nc);
-      const float f1 = fmaf(ptx::ex2_approx(z1), c, nc);
-      const uint32_t fp = kFp16 ? ptx::pack_f16_sat(f0, f1) : ptx::pack_bf16(f0, f1);
-      p[j] = kFp16 ? ptx::select_neg_f16x2(zp, fp) : ptx::select_neg_bf16x2(zp, fp);
-    } else {
-      p[j] = zp;
-    }
-  }
+// c*(2^z - 1) for z < 0 on a packed fp16 pair without the MUFU: clamp at -13 (2^-13 is below the resolution of the
+// result), split z = -k + r with the 1536 = 1.5*2^10 rounding trick (k = 0..13 lands in the low mantissa bits of u),
+// degree-3 polynomial for 2*2^r on [-0.5, 0.5] (the factor 2 keeps every pair's exponent field >= k, so the packed
+// integer subtraction of k << 10 never borrows across the halves, whatever garbage a discarded z >= 0 lane holds),
+// then (c/2)*p - c as one HFMA2: 10 instructions after the pack, none on the MUFU.  Max abs error 9.1e-4 over all
+// negative fp16 inputs vs 8.4e-4 for a correctly rounded 2^z followed by the same HFMA2 (exhaustive CPU emulation,
+// scripts/experiments/polyelu.py).
+__device__ __forceinline__ uint32_t elu_neg_poly_f16x2(uint32_t z, uint32_t ch2, uint32_t nc2) {
+  const uint32_t kM = 0x66006600u;                        // (1536, 1536)
+  const uint32_t zc = ptx::max_f16x2(z, 0xCA80CA80u);     // max(z, -13)
+  const uint32_t u = ptx::sub_f16x2(kM, zc);              // 1536 + k, k = round(-zc)
+  const uint32_t r = ptx::add_f16x2(zc, ptx::sub_f16x2(u, kM));
+  uint32_t p = ptx::fma_f16x2(0x2F102F10u, r, 0x37C337C3u);   // 0.11035 r + 0.48511
+  p = ptx::fma_f16x2(p, r, 0x3D8C3D8Cu);                      // ... + 1.38672
+  p = ptx::fma_f16x2(p, r, 0x40004000u);                      // ... + 2.0
+  p -= (u & 0x000F000Fu) << 10;                               // * 2^-k
+  return ptx::fma_f16x2(p, ch2, nc2);
 }
 
-// same on 16 accumulator columns -> 8 packed words
-constexpr int kTcPolyPairs = GO2P_TC_POLY_PAIRS;   // of every 8 column pairs, this many take the FMA-pipe exponential
+// same on 16 accumulator columns -> 8 packed words.  fp16: every pair stays packed -- F2FP (pack z'), then either
+// ex2.approx.f16x2 (2 MUFU + PRMT) + HFMA2 (c*e - c) or, for the pairs selected by GO2P_TC_POLYMASK, the FMA-pipe
+// polynomial above; HSET2 + LOP3 select.  bf16 keeps the fp32 exponential everywhere (its budget has no slack).
+#ifndef GO2P_TC_POLYMASK
+#define GO2P_TC_POLYMASK 0x88u     // bit j: column pair j of every 8 takes the FMA-pipe exponential (2 of 8)
+#endif
 
 template <bool kFp16>
 __device__ __forceinline__ void elu_pack16(const uint32_t (&v)[16], bool has_elu, float c, uint32_t (&p)[8]) {
   const float nc = -c;
+  if constexpr (kFp16) {
+    const uint32_t c2 = ptx::pack_f16_sat(c, c), nc2 = ptx::pack_f16_sat(nc, nc), ch2 = ptx::pack_f16_sat(0.5f * c, 0.5f * c);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float z0 = __uint_as_float(v[2 * j]), z1 = __uint_as_float(v[2 * j + 1]);
-    const uint32_t zp = kFp16 ? ptx::pack_f16_sat(z0, z1) : ptx::pack_bf16(z0, z1);
-    if (has_elu) {
-      const bool poly = kFp16 && j >= 8 - kTcPolyPairs;   // bf16 keeps the MUFU everywhere (its budget has no slack)
-      if (GO2P_TC_HALF_ELU && kFp16 && !poly) {
-        // packed pair all the way: 2^z on the fp16 pair, c*e - c as one HFMA2 (6 instead of 8 instructions per pair)
-        const uint32_t c2 = ptx::pack_f16_sat(c, c), nc2 = ptx::pack_f16_sat(nc, nc);
-        p[j] = ptx::select_neg_f16x2(zp, ptx::fma_f16x2(ptx::ex2_f16x2(zp), c2, nc2));
-        continue;
-      }
-      const float f0 = fmaf(poly ? ptx::ex2_poly(z0) : ptx::ex2_approx(z0), c, nc);
-      const float f1 = fmaf(poly ? ptx::ex2_poly(z1) : ptx::ex2_approx(z1), c, nc);
-      const uint32_t fp = kFp16 ? ptx::pack_f16_sat(f0, f1) : ptx::pack_bf16(f0, f1);
-      p[j] = kFp16 ? ptx::select_neg_f16x2(zp, fp) : ptx::select_neg_bf16x2(zp, fp);
-    } else {
-      p[j] = zp;
-    }
-  }
-}
-
-template <bool kFp16>
-__device__ __forceinline__ void elu_pack32(const uint32_t (&v)[32], bool has_elu, float c, uint32_t (&p)[16]) {
-  if (has_elu) {
-    const float nc = -c;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float z0 = __uint_as_float(v[2 * j]), z1 = __uint_as_float(v[2 * j + 1]);
-      const float f0 = fmaf(ptx::ex2_approx(z0), c, nc);
-      const float f1 = fmaf(ptx::ex2_approx(z1), c, nc);
-      if (kFp16) {
-        const uint32_t zp = ptx::pack_f16_sat(z0, z1), fp = ptx::pack_f16_sat(f0, f1);
-        p[j] = ptx::select_neg_f16x2(zp, fp);
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t zp = ptx::pack_f16_sat(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+      if (has_elu) {
+        const uint32_t f = ((GO2P_TC_POLYMASK >> j) & 1u) ? elu_neg_poly_f16x2(zp, ch2, nc2)
+                                                         : ptx::fma_f16x2(ptx::ex2_f16x2(zp), c2, nc2);
+        p[j] = ptx::select_neg_f16x2(zp, f);
       } else {
-        const uint32_t zp = ptx::pack_bf16(z0, z1), fp = ptx::pack_bf16(f0, f1);
-        p[j] = ptx::select_neg_bf16x2(zp, fp);
+        p[j] = zp;
       }
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < 8; ++j) {
       const float z0 = __uint_as_float(v[2 * j]), z1 = __uint_as_float(v[2 * j + 1]);
-      p[j] = kFp16 ? ptx::pack_f16_sat(z0, z1) : ptx::pack_bf16(z0, z1);
+      const uint32_t zp = ptx::pack_bf16(z0, z1);
+      if (has_elu) {
+        const float f0 = fmaf(ptx::ex2_approx(z0), c, nc);
+        const float f1 = fmaf(ptx::ex2_approx(z1), c, nc);
+        p[j] = ptx::select_neg_bf16x2(zp, ptx::pack_bf16(f0, f1));
+      } else {
+        p[j] = zp;
+      }
     }
   }
 }
@@ -226,7 +202,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
   uint8_t* stage0 = smem + wbytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + 2 * stage_bytes);
   uint64_t* obs_full = bars;        // [2]
-  uint64_t* obs_empty = bars + 2;   // [2]
   uint64_t* acc_full = bars + 4;    // [2]
   uint64_t* a_blk = bars + 6;       // [2][4], entry [s][0] used: A operand of slot s's next layer ready (16 arrivals)
   uint64_t* w_full = bars + 14;     // [kMaxLayers]  layer weights landed in shared memory (completes once)
@@ -355,6 +330,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
     const bool even = (a.in_dim & 1) == 0;
 
     uint32_t par_acc[2] = {0u, 0u};
+    const bool masked = (a.flags & 1u) && a.button0 != nullptr;
+    int b0_s0 = 0, b0_s1 = 0;                // dead-man buttons of this thread's row in the two slots' tiles
     // ---- conv(s): fp32 observation rows -> 16-bit layer-0 A operand, constant ones at K = in_dim, in_dim+1.
     //      chunk c8 (16 K elements = 8 columns) lands at 32*(c8/2) + 8*(c8%2) of buffer phi: block cb = chunks 2cb, 2cb+1
     auto conv_job = [&](int pair, int s) {
@@ -419,7 +396,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
 #pragma unroll
             for (int j = 0; j < 4; ++j) o[j] = __uint_as_float(v[j]);
             if (a.flags & 1u) {
-              const int b0 = a.button0 ? a.button0[row] : 0;
+              const int b0 = s ? b0_s1 : b0_s0;          // loaded two jobs ahead (see the E loop)
 #pragma unroll
               for (int j = 0; j < 4; ++j) o[j] = clamp_mask(o[j], a.action_limit, b0);
             }
@@ -454,6 +431,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
       for (int l = 0; l < L; ++l) {
         const bool he = a.has_elu[l] != 0;
         const float c = a.elu_c[l];
+        if (l == L - 1 && masked) {
+          // the output jobs of this pair need the rows' dead-man buttons: request them two jobs ahead, so the global
+          // load is not waited for in the output job (it was 9 % of the pool's time)
+          const long long r0 = (blockIdx.x + (long long)(pair * 2) * gridDim.x) * kTcTileM + m;
+          const long long r1 = r0 + (long long)gridDim.x * kTcTileM;
+          b0_s0 = r0 < a.B ? __ldg(a.button0 + r0) : 0;
+          b0_s1 = r1 < a.B ? __ldg(a.button0 + r1) : 0;
+        }
         for (int s = 0; s < ns; ++s) {
           const uint32_t d_t = tmem_base + (uint32_t)s * kTcSlotCols + lane_addr + 128u * (uint32_t)((phi + 1 + l) & 1) + (uint32_t)(cb * 32);
           ptx::mbar_wait(&acc_full[s], par_acc[s]);

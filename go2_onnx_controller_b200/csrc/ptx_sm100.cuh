@@ -73,6 +73,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// the same operations on 32-bit shared-window addresses (no generic -> shared conversion per call)
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_test_wait_u32(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .pred q;\n\t.reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n"
+      "GO2P_WAITU:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra GO2P_DONEU;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 q, n, 0x2000000;\n\t"
+      "@q bra GO2P_WAITU;\n\t"
+      "trap;\n"
+      "GO2P_DONEU:\n\t}"
+      ::"r"(bar), "r"(parity) : "memory");
+}
+
 // generic-proxy smem writes -> visible to the async proxy (tensor core / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -138,11 +166,7 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-#ifdef GO2P_EXP_NOWAITST
-__device__ __forceinline__ void tc_wait_st() {}   // timing experiment only: unsafe ordering
-#else
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-#endif
 
 // ------------------------------------------------------------------ tcgen05: descriptors
 // Shared-memory matrix descriptor, K-major operand, SWIZZLE_NONE ("interleaved" 8x16B core matrices):
@@ -271,6 +295,22 @@ __device__ __forceinline__ uint32_t fma_f16x2(uint32_t a, uint32_t b, uint32_t c
   asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
   return r;
 }
+__device__ __forceinline__ uint32_t add_f16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t sub_f16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+// per half: the larger operand; a NaN operand yields the other one
+__device__ __forceinline__ uint32_t max_f16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
 // 2^x for x <= 0 on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + r via the 1.5*2^23 trick,
 // degree-3 minimax polynomial for 2^r on [-0.5, 0.5] (max relative error 7.5e-5, below half an fp16 ulp), exponent
 // patched in with an integer add.  Inputs below -24 are clamped (2^-24 is far below the resolution of c*(2^x - 1));
@@ -286,9 +326,6 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
 }
 __device__ __forceinline__ float ex2_approx(float x) {
-#ifdef GO2P_EXP_NOMUFU
-  return x + 1.0f;   // timing experiment only: wrong numerics, no MUFU
-#endif
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;

@@ -1,4 +1,5 @@
-"""Timeline of one CTA of tc_mlp_kernel (trace build: -DGO2P_TC_TRACE).  Prints per-event clock deltas."""
+"""Timeline of one CTA of tc_mlp_kernel (trace build: -DGO2P_TC_TRACE, lib/libgo2policy_trace.so).
+usage: tc_trace.py [rows] [first event] [count] [warps, comma separated]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -9,6 +10,9 @@ os.environ["GO2P_TC_TRACE_PTR"] = str(trace.data_ptr())
 import go2_onnx_controller_b200 as pkg
 from go2_onnx_controller_b200 import capi
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1_048_576
+lo = int(sys.argv[2]) if len(sys.argv) > 2 else 320
+cnt = int(sys.argv[3]) if len(sys.argv) > 3 else 64
+warps = [int(w) for w in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0, 16]
 pb = pkg.PolicyBatch(pkg.DEFAULT_MODEL)
 d_obs = torch.randn((B, 98), device="cuda"); d_act = torch.empty((B, 12), device="cuda")
 for _ in range(3):
@@ -17,17 +21,16 @@ for _ in range(3):
     pb.infer_device(d_obs.data_ptr(), d_act.data_ptr(), B, capi.PREC_FP16)
     torch.cuda.synchronize()
 t = trace.cpu().numpy().reshape(34, 2048)
-evs, cks = [], []
-for w in range(34):
-    n = int(t[w, 2046])
-    evs.append(t[w, 0:2 * n:2]); cks.append(t[w, 1:2 * n:2])
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 np.save(os.path.join(ROOT, "gpurun_out", "tc_trace_raw.npy"), t)
-ev = np.concatenate(evs); ck = np.concatenate(cks); n = ev.size
-order = np.argsort(ck, kind="stable"); ev = ev[order]; ck = ck[order] - ck[order][0]
-names = {1: "P issue", 2: "M ready", 3: "M commit", 4: "E obs_full", 5: "E L0 done", 6: "E acc_full", 7: "E layer done", 8: "E out start", 9: "E out done"}
-np.save(os.path.join(ROOT, "gpurun_out", "tc_trace.npy"), np.stack([ev, ck]))
-print("events", n, "span cycles", ck[-1])
-lo = int(sys.argv[2]) if len(sys.argv) > 2 else 400
-for e, c in list(zip(ev, ck))[lo:lo + 75]:
-    k = int(e) >> 8; l = (int(e) >> 4) & 7; s = int(e) & 1; w7 = (int(e) >> 3) & 1
-    print(f"{c:9d}  {names.get(k, hex(e)):14s} slot {s} layer {l} {'(wq7)' if w7 else ''}")
+names = {1: "C tma issue", 2: "C a_ready", 3: "C committed", 4: "W conv acquired", 6: "W E acquired", 7: "W arrived", 8: "W out acquired",
+         9: "W out done", 10: "W A buffer free", 11: "W st drained", 12: "W next acquired", 15: "W fine"}
+c0 = min(int(t[w, 1]) for w in range(17) if t[w, 2046] > 0)
+for w in warps:
+    n = int(t[w, 2046]); ev = t[w, 0:2 * n:2]; ck = t[w, 1:2 * n:2]
+    print(f"--- warp {w}: {n} events, span {int(ck[-1] - ck[0])} cycles")
+    prev = None
+    for e, c in list(zip(ev, ck))[(lo if w < 16 else lo * 13 // 19):][:cnt]:
+        e = int(e); k = e >> 8; l = (e >> 4) & 15; s = e & 3
+        print(f"{int(c) - c0:9d} (+{(int(c) - prev) if prev else 0:5d}) {names.get(k, hex(e)):16s} slot {s} sub {l}")
+        prev = int(c)
