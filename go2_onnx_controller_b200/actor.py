@@ -109,6 +109,25 @@ class Go2Controller:
         capi.check(self._hd.lib.go2p_step_fused(self._hd.h, C.byref(raw), C.byref(out)))
         return out
 
+    def step_cmd(self, raw: capi.RawState):
+        """step() plus the same step's send_command arguments in Unitree motor order (controller.cpp:235-251)."""
+        out, cmd = capi.StepOut(), capi.MotorCmd()
+        capi.check(self._hd.lib.go2p_step_fused_cmd(self._hd.h, C.byref(raw), C.byref(out), C.byref(cmd)))
+        return out, cmd
+
+    def log_enable(self, capacity: int) -> None:
+        """ObservationAction ring on the device (ObservationAction.msg:1-2); 0 turns it off."""
+        capi.check(self._hd.lib.go2p_log_enable(self._hd.h, int(capacity)))
+
+    def log_drain(self, max_records: int = 4096):
+        """Records written since the last drain, oldest first: ([n, in_dim] observations, [n, 12] actions, dropped)."""
+        rec = self._hd.in_dim + 12
+        buf = np.zeros((max_records, rec), np.float32)
+        n, dropped = C.c_int(), C.c_uint64()
+        capi.check(self._hd.lib.go2p_log_drain(self._hd.h, buf.ctypes.data, max_records, C.byref(n), C.byref(dropped)))
+        buf = buf[: n.value]
+        return buf[:, : self._hd.in_dim].copy(), buf[:, self._hd.in_dim:].copy(), int(dropped.value)
+
     def closed_loop(self, raws, steps: int):
         """`steps` fused steps over the raw states (cycled), timed in native code.
         Returns (host_ns[steps], device_ns[steps], last StepOut)."""
@@ -160,10 +179,11 @@ class PolicyBatch:
     def info(self) -> capi.ModelInfo:
         return self._hd.info
 
-    def infer_device(self, d_obs: int, d_act: int, B: int, precision: int = capi.PREC_BF16, stream: int = 0,
-                     d_button0: int | None = None, d_qdes: int | None = None, flags: int = 0) -> None:
-        capi.check(self._hd.lib.go2p_infer_batch_ex(self._hd.h, d_obs, d_button0, d_act, d_qdes, B, precision, flags,
-                                                    stream or None))
+    def infer_device(self, d_obs: int, d_act: int, B: int, precision: int = capi.PREC_FP32, stream: int = 0,
+                     d_button0: int | None = None, d_qdes: int | None = None, flags: int = 0, d_cmd: int | None = None) -> None:
+        """precision defaults to the reference's (fp32, 1e-5 contract); the tensor-core precisions are opt-in."""
+        capi.check(self._hd.lib.go2p_infer_batch_cmd(self._hd.h, d_obs, d_button0, d_act, d_qdes, d_cmd, B, precision, flags,
+                                                     stream or None))
 
     def time_device(self, d_obs: int, d_act: int, B: int, precision: int, iters: int, stream: int = 0,
                     d_button0: int | None = None, d_qdes: int | None = None, flags: int = 0) -> float:
@@ -172,7 +192,7 @@ class PolicyBatch:
                                                 stream or None, iters, C.byref(ms)))
         return float(ms.value)
 
-    def infer_host(self, obs: np.ndarray, act: np.ndarray | None = None, precision: int = capi.PREC_BF16) -> np.ndarray:
+    def infer_host(self, obs: np.ndarray, act: np.ndarray | None = None, precision: int = capi.PREC_FP32) -> np.ndarray:
         obs = np.ascontiguousarray(obs, np.float32).reshape(-1, self.in_dim)
         if act is None:
             act = np.empty((obs.shape[0], self.out_dim), np.float32)
@@ -200,5 +220,60 @@ class PolicyBatch:
         capi.check(self._hd.lib.go2p_step_batch(self._hd.h, d_raw, d_vel_cmd, d_obs, d_action, d_qdes, B, precision,
                                                 stream or None))
 
+    def step_device_cmd(self, d_raw: int, d_vel_cmd: int, d_obs: int, d_action: int, d_qdes: int | None, d_cmd: int | None,
+                        B: int, precision: int = capi.PREC_FP32, stream: int = 0) -> None:
+        """step_device ending in motor commands: d_cmd [B] go2p_motor_cmd (Unitree motor order), d_qdes may be None."""
+        capi.check(self._hd.lib.go2p_step_batch_cmd(self._hd.h, d_raw, d_vel_cmd, d_obs, d_action, d_qdes, d_cmd, B, precision,
+                                                    stream or None))
+
+    def step_host(self, raw: np.ndarray, action: np.ndarray, cmd: np.ndarray | None = None,
+                  precision: int = capi.PREC_FP32) -> None:
+        """Closed-loop step for len(raw) robots from host buffers; per-robot history stays on the device.
+        raw: uint8 [B, 156] (go2p_raw_state records), action: float32 [B, 12] out, cmd: uint8 [B, 112] out or None."""
+        B = raw.shape[0]
+        capi.check(self._hd.lib.go2p_step_batch_host(self._hd.h, raw.ctypes.data, action.ctypes.data,
+                                                     cmd.ctypes.data if cmd is not None else None, B, precision))
+
+    def step_host_reset(self) -> None:
+        capi.check(self._hd.lib.go2p_step_batch_host_reset(self._hd.h))
+
     def close(self) -> None:
         self._hd.close()
+
+
+class Fleet:
+    """One process, several GPUs: rows are split into contiguous shards, one handle + host thread per device
+    (include/go2policy.h: go2p_fleet_*).  No data crosses between devices."""
+
+    def __init__(self, model_path: str = DEFAULT_MODEL, devices=(0,), **cfg):
+        self.lib = capi.load()
+        self.f = C.c_void_p()
+        c = default_config(**cfg)
+        dev = (C.c_int32 * len(devices))(*devices)
+        capi.check(self.lib.go2p_fleet_create(os.fspath(model_path).encode(), C.byref(c), dev, len(devices), C.byref(self.f)))
+        self.n_devices = len(devices)
+
+    def infer_host(self, obs: np.ndarray, act: np.ndarray, precision: int = capi.PREC_FP32) -> None:
+        capi.check(self.lib.go2p_fleet_infer_host(self.f, obs.ctypes.data, act.ctypes.data, obs.shape[0], precision))
+
+    def step_host(self, raw: np.ndarray, action: np.ndarray, cmd: np.ndarray | None = None, precision: int = capi.PREC_FP32) -> None:
+        capi.check(self.lib.go2p_fleet_step_host(self.f, raw.ctypes.data, action.ctypes.data,
+                                                 cmd.ctypes.data if cmd is not None else None, raw.shape[0], precision))
+
+    def close(self) -> None:
+        if self.f:
+            self.lib.go2p_fleet_destroy(self.f)
+            self.f = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def shard_rows(total_rows: int, n: int, i: int):
+    """(begin, end) of shard i of n as the C ABI splits them (go2p_shard_rows)."""
+    b, e = C.c_int64(), C.c_int64()
+    capi.check(capi.load().go2p_shard_rows(total_rows, n, i, C.byref(b), C.byref(e)))
+    return b.value, e.value

@@ -12,11 +12,11 @@ GO2P_MAX_HISTORY = 8
 GO2P_MAX_LAYERS = 8
 
 OK, ERR_INVALID, ERR_IO, ERR_MODEL, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_STATE, ERR_TIMEOUT = range(9)
-PREC_FP32, PREC_BF16, PREC_FP16, PREC_TF32 = 0, 1, 2, 3
+PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
 B1_PERSISTENT, B1_GRAPH, B1_LAUNCH = 0, 1, 2
-F_CLAMP_MASK, F_QDES = 1, 2
+F_CLAMP_MASK, F_QDES, F_MOTOR_CMD = 1, 2, 4
 
-PREC_NAMES = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16, "tf32": PREC_TF32}
+PREC_NAMES = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16}
 
 
 class Config(C.Structure):
@@ -41,6 +41,11 @@ class StepOut(C.Structure):
         ("action", C.c_float * 12), ("q_des", C.c_double * 12), ("kp", C.c_double), ("kd", C.c_double),
         ("device_ns", C.c_uint64),
     ]
+
+
+class MotorCmd(C.Structure):
+    """send_command arguments in Unitree motor order (include/go2policy.h: go2p_motor_cmd)."""
+    _fields_ = [("q_des", C.c_double * GO2P_DOF), ("kp", C.c_double), ("kd", C.c_double)]
 
 
 class ModelInfo(C.Structure):
@@ -88,6 +93,22 @@ SIGNATURES = {
     "go2p_step_batch": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                   C.c_void_p]),
     "go2p_last_launch_count": (C.c_int, [_H]),
+    "go2p_infer_batch_cmd": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                        C.c_uint32, C.c_void_p]),
+    "go2p_step_batch_cmd": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                       C.c_int, C.c_void_p]),
+    "go2p_step_fused_cmd": (C.c_int, [_H, C.POINTER(RawState), C.POINTER(StepOut), C.POINTER(MotorCmd)]),
+    "go2p_motor_order": (C.c_int, [C.POINTER(C.c_int32)]),
+    "go2p_step_batch_host": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
+    "go2p_step_batch_host_reset": (C.c_int, [_H]),
+    "go2p_log_enable": (C.c_int, [_H, C.c_int]),
+    "go2p_log_drain": (C.c_int, [_H, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
+    "go2p_fleet_create": (C.c_int, [C.c_char_p, C.POINTER(Config), C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_void_p)]),
+    "go2p_fleet_destroy": (C.c_int, [C.c_void_p]),
+    "go2p_fleet_device_count": (C.c_int, [C.c_void_p]),
+    "go2p_shard_rows": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "go2p_fleet_infer_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
+    "go2p_fleet_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     "go2p_dev_alloc": (C.c_int, [_H, C.c_size_t, C.POINTER(C.c_void_p)]),
     "go2p_dev_free": (C.c_int, [_H, C.c_void_p]),
     "go2p_host_alloc": (C.c_int, [_H, C.c_size_t, C.POINTER(C.c_void_p)]),

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
+#include <thread>
 #include <string>
 #include <vector>
 #if defined(__x86_64__)
@@ -29,6 +30,7 @@
 using namespace go2p;
 
 static_assert(sizeof(go2p_raw_state) == sizeof(RawStateDev), "raw state layout");
+static_assert(sizeof(go2p_motor_cmd) == sizeof(MotorCmdDev), "motor command layout");
 
 namespace {
 
@@ -103,6 +105,18 @@ struct go2p_handle {
   float* pipe_in[kPipeDepth] = {};
   float* pipe_out[kPipeDepth] = {};
   int last_launches = 0;
+  // ObservationAction ring (go2p_log_enable)
+  LogRing* d_log = nullptr;
+  uint32_t log_capacity = 0;
+  uint64_t log_tail = 0;
+  // go2p_step_batch_host: per-robot state resident on the device + staging of the raw states / commands
+  struct Fleet {
+    int64_t robots = 0;
+    float* obs = nullptr; float* vel = nullptr; float* act = nullptr;
+    go2p_raw_state* raw[kPipeDepth] = {};
+    MotorCmdDev* cmd[kPipeDepth] = {};
+    int32_t* button[kPipeDepth] = {};
+  } fleet;
 };
 
 namespace {
@@ -206,6 +220,8 @@ int upload_model(go2p_handle* h) {
   h->cc.kp_deadman = h->cfg.kp_deadman;
   h->cc.foot_threshold = h->cfg.foot_threshold;
   h->cc.H = h->cfg.history;
+  h->cc.kp = h->cfg.kp;
+  h->cc.kd = h->cfg.kd;
 
   // ---- tensor-core packing (narrow family: every hidden width 128, in + 2 <= 128, out <= 16: the layer-0 operand
   // with its two constant-one columns has to fit the 64 packed columns of a TMEM buffer; wider inputs take the
@@ -276,6 +292,7 @@ B1Args make_b1_args(const go2p_handle* h, bool weights_in_smem) {
   a.weights_in_smem = weights_in_smem ? 1 : 0;
   a.idle_ns = (unsigned long long)std::max(0, h->cfg.idle_exit_ms) * 1000000ull;
   a.epoch = h->epoch;
+  a.log = h->d_log;
   return a;
 }
 
@@ -387,7 +404,7 @@ int ensure_scratch(go2p_handle* h, int64_t rows) {
 }
 
 int launch_fp32(go2p_handle* h, const float* d_obs, const int32_t* d_button0, float* d_act, double* d_qdes,
-                int64_t B, uint32_t flags, cudaStream_t st) {
+                MotorCmdDev* d_cmd, int64_t B, uint32_t flags, cudaStream_t st) {
   const DevModel& dm = h->dm;
   const int64_t chunk = std::min<int64_t>(B, kFp32ChunkRows);
   int rc = ensure_scratch(h, chunk);
@@ -401,12 +418,17 @@ int launch_fp32(go2p_handle* h, const float* d_obs, const int32_t* d_button0, fl
       const bool last = l == dm.n_layers - 1;
       float* out = last ? d_act + r0 * dm.out_dim : h->scratch_sets[h->scratch_sel].buf[l & 1];
       const int ldc = L.N;
-      if (last && L.N <= 32) {
-        const size_t smem = ((size_t)kSoRows * (L.K | 1) + (size_t)L.N * L.Kp) * sizeof(float);
-        CU_TRY(cudaFuncSetAttribute(small_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        small_out_kernel<<<(unsigned)((rows + kSoRows - 1) / kSoRows), kSoRows, smem, st>>>(
+      // the narrow output kernel stages 128 whole rows in shared memory: it serves last hidden widths up to ~440;
+      // wider ones take the generic GEMM + the elementwise A9/A11 kernel
+      const size_t so_smem = ((size_t)kSoRows * (L.K | 1) + (size_t)L.N * L.Kp) * sizeof(float);
+      if (last && L.N <= 32 && so_smem <= (size_t)227 * 1024) {
+        if (h->so_attr_smem < so_smem) {
+          CU_TRY(cudaFuncSetAttribute(small_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)so_smem));
+          h->so_attr_smem = so_smem;
+        }
+        small_out_kernel<<<(unsigned)((rows + kSoRows - 1) / kSoRows), kSoRows, so_smem, st>>>(
             in, lda, L.w_rm, L.Kp, L.bias, out, ldc, rows, L.K, L.N, L.has_elu, L.alpha, flags,
-            d_button0 ? d_button0 + r0 : nullptr, d_qdes ? d_qdes + r0 * kDof : nullptr, h->cc);
+            d_button0 ? d_button0 + r0 : nullptr, d_qdes ? d_qdes + r0 * kDof : nullptr, d_cmd ? d_cmd + r0 : nullptr, h->cc);
         h->last_launches++;
       } else {
         dim3 grid((unsigned)((rows + kSgBM - 1) / kSgBM), (unsigned)(L.Np / kSgBN));
@@ -417,7 +439,8 @@ int launch_fp32(go2p_handle* h, const float* d_obs, const int32_t* d_button0, fl
           const long long total = rows * (long long)dm.out_dim;
           post_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, total, dm.out_dim, flags,
                                                                       d_button0 ? d_button0 + r0 : nullptr,
-                                                                      d_qdes ? d_qdes + r0 * kDof : nullptr, h->cc);
+                                                                      d_qdes ? d_qdes + r0 * kDof : nullptr,
+                                                                      d_cmd ? d_cmd + r0 : nullptr, h->cc);
           h->last_launches++;
         }
       }
@@ -446,13 +469,14 @@ int launch_tc_t(go2p_handle* h, const TcArgs& a, cudaStream_t st) {
   return GO2P_OK;
 }
 
-int launch_tc(go2p_handle* h, const float* d_obs, const int32_t* d_button0, float* d_act, double* d_qdes, int64_t B,
-              bool fp16, uint32_t flags, cudaStream_t st) {
+int launch_tc(go2p_handle* h, const float* d_obs, const int32_t* d_button0, float* d_act, double* d_qdes,
+              MotorCmdDev* d_cmd, int64_t B, bool fp16, uint32_t flags, cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(d_obs) & 15) || (reinterpret_cast<uintptr_t>(d_act) & 15) ||
       (d_qdes && (reinterpret_cast<uintptr_t>(d_qdes) & 15)))
     return fail(GO2P_ERR_INVALID, "tensor-core path needs 16-byte aligned obs/act/qdes device pointers");
   TcArgs a{};
   a.obs = d_obs; a.act = d_act; a.button0 = d_button0; a.qdes = d_qdes; a.B = B;
+  a.cmd = d_cmd; a.kp = h->cc.kp; a.kd = h->cc.kd; a.kp_deadman = h->cc.kp_deadman;
   a.wpack = h->d_wpack[fp16 ? 1 : 0];
   a.n_layers = h->dm.n_layers; a.in_dim = h->dm.in_dim; a.k0p = h->k0p; a.out_dim = h->dm.out_dim;
   for (int l = 0; l < h->dm.n_layers; ++l) {
@@ -471,6 +495,31 @@ int launch_tc(go2p_handle* h, const float* d_obs, const int32_t* d_button0, floa
   return fp16 ? launch_tc_t<true>(h, a, st) : launch_tc_t<false>(h, a, st);
 }
 
+}  // namespace
+
+struct go2p_fleet {
+  std::vector<go2p_handle*> handles;
+};
+
+namespace {
+// one host thread per device: each drives its own handle (its own streams and scratch) on its shard of the rows
+template <class Fn>
+int fleet_run(go2p_fleet* f, int64_t B, Fn&& per_shard) {
+  const int n = (int)f->handles.size();
+  std::vector<int> rc(n, GO2P_OK);
+  std::vector<std::string> msg(n);
+  std::vector<std::thread> threads;
+  for (int i = 0; i < n; ++i) {
+    threads.emplace_back([&, i]() {
+      int64_t b = 0, e = 0;
+      go2p_shard_rows(B, n, i, &b, &e);
+      if (e > b) { rc[i] = per_shard(f->handles[i], b, e - b); if (rc[i]) msg[i] = g_err; }   // g_err is thread-local
+    });
+  }
+  for (auto& t : threads) t.join();
+  for (int i = 0; i < n; ++i) if (rc[i]) return fail(rc[i], "device shard " + std::to_string(i) + ": " + msg[i]);
+  return GO2P_OK;
+}
 }  // namespace
 
 // =============================================================================================
@@ -547,6 +596,8 @@ int go2p_create(const char* onnx_path, const go2p_config* cfg_in, go2p_handle** 
   if (rc == GO2P_OK) {
     h->n_in_slots = round_up(std::max(h->dm.in_dim, kRawWords), 32);
     if (h->n_in_slots > kB1Threads) rc = fail(GO2P_ERR_UNSUPPORTED, "batch-1 path supports in_dim <= 512");
+    // MSG_ACT answers out_dim words + two timing words, one per thread, below the farewell slot
+    else if (h->dm.out_dim + 2 > std::min(kB1Threads, kByeSlot)) rc = fail(GO2P_ERR_UNSUPPORTED, "batch-1 path supports out_dim <= 510");
   }
   auto cuda_part = [&]() -> int {
     CU_TRY(cudaStreamCreateWithFlags(&h->b1_stream, cudaStreamNonBlocking));
@@ -592,6 +643,13 @@ int go2p_destroy(go2p_handle* h) {
     for (int i = 0; i < 2; ++i) if (sc.buf[i]) cudaFree(sc.buf[i]);
   if (h->d_state) cudaFree(h->d_state);
   if (h->d_step_button) cudaFree(h->d_step_button);
+  if (h->d_log) cudaFree(h->d_log);
+  for (void* p : {(void*)h->fleet.obs, (void*)h->fleet.vel, (void*)h->fleet.act}) if (p) cudaFree(p);
+  for (int i = 0; i < kPipeDepth; ++i) {
+    if (h->fleet.raw[i]) cudaFree(h->fleet.raw[i]);
+    if (h->fleet.cmd[i]) cudaFree(h->fleet.cmd[i]);
+    if (h->fleet.button[i]) cudaFree(h->fleet.button[i]);
+  }
   if (h->inbox) cudaFreeHost(h->inbox);
   if (h->outbox) cudaFreeHost(h->outbox);
   delete h;
@@ -756,6 +814,19 @@ int go2p_step_fused(go2p_handle* h, const go2p_raw_state* raw, go2p_step_out* ou
   return GO2P_OK;
 }
 
+// the send_command arguments of the same step in Unitree motor order (data movement only: the values are the kernel's)
+int go2p_step_fused_cmd(go2p_handle* h, const go2p_raw_state* raw, go2p_step_out* out, go2p_motor_cmd* cmd) {
+  if (!cmd) return fail(GO2P_ERR_INVALID, "go2p_step_fused_cmd: null argument");
+  go2p_step_out local;
+  go2p_step_out* o = out ? out : &local;
+  const int rc = go2p_step_fused(h, raw, o);
+  if (rc) return rc;
+  for (int i = 0; i < GO2P_DOF; ++i) cmd->q_des[motor_of_isaac(i)] = o->q_des[i];
+  cmd->kp = o->kp;
+  cmd->kd = o->kd;
+  return GO2P_OK;
+}
+
 int go2p_b1_closed_loop(go2p_handle* h, const go2p_raw_state* raws, int n_raws, int steps, uint64_t* host_ns,
                         uint64_t* device_ns, go2p_step_out* last) {
   if (!h || !raws || n_raws < 1 || steps < 0) return fail(GO2P_ERR_INVALID, "go2p_b1_closed_loop: bad argument");
@@ -820,7 +891,8 @@ int go2p_b1_selfdriven(go2p_handle* h, const go2p_raw_state* raws, int n_raws, i
   if (last_action) CU_TRY(cudaMemcpyAsync(last_action, d_out, 48, cudaMemcpyDeviceToHost, h->pipe_stream[0]));
   CU_TRY(cudaStreamSynchronize(h->pipe_stream[0]));
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  if (!h->resident) { cudaFree(d_raws); cudaFree(d_out); cudaFree(d_st); }   // cudaFree would block on a resident kernel
+  if (!h->resident) { cudaFree(d_raws); cudaFree(d_out); cudaFree(d_st); }
+  else { h->dev_owned.push_back(d_raws); h->dev_owned.push_back(d_out); h->dev_owned.push_back(d_st); }   // cudaFree would block on the resident kernel: retired, freed by go2p_destroy
   h->last_launches = 1;
   return GO2P_OK;
 }
@@ -835,6 +907,8 @@ int go2p_set_gains(go2p_handle* h, float kp, float kd) {
   uint32_t w[2];
   std::memcpy(&w[0], &kp, 4);
   std::memcpy(&w[1], &kd, 4);
+  h->cfg.kp = h->cc.kp = kp;       // the batched epilogues read the gains from the handle
+  h->cfg.kd = h->cc.kd = kd;
   return simple_message(h, MSG_GAINS, w, 2);
 }
 
@@ -847,42 +921,55 @@ int go2p_b1_stats_get(go2p_handle* h, go2p_b1_stats* out, int reset) {
 }
 
 // ------------------------------------------------------------------------------------- batched
-int go2p_infer_batch_ex(go2p_handle* h, const float* d_obs, const int32_t* d_button0, float* d_act, double* d_qdes,
-                        int64_t B, int precision, uint32_t flags, void* stream) {
+int go2p_infer_batch_cmd(go2p_handle* h, const float* d_obs, const int32_t* d_button0, float* d_act, double* d_qdes,
+                         go2p_motor_cmd* d_cmd, int64_t B, int precision, uint32_t flags, void* stream) {
   if (!h) return fail(GO2P_ERR_INVALID, "go2p_infer_batch: null handle");
   if (B < 0) return fail(GO2P_ERR_INVALID, "negative batch");
   if (B == 0) { h->last_launches = 0; return GO2P_OK; }   // empty batch: nothing is read, nothing is launched
   if (!d_obs || !d_act) return fail(GO2P_ERR_INVALID, "go2p_infer_batch: null argument");
   if ((flags & GO2P_F_QDES) && (!d_qdes || h->dm.out_dim != GO2P_DOF))
     return fail(GO2P_ERR_INVALID, "GO2P_F_QDES needs d_qdes and a 12-output policy");
+  if ((flags & GO2P_F_MOTOR_CMD) && (!d_cmd || h->dm.out_dim != GO2P_DOF))
+    return fail(GO2P_ERR_INVALID, "GO2P_F_MOTOR_CMD needs d_cmd and a 12-output policy");
+  if ((flags & GO2P_F_MOTOR_CMD) && (reinterpret_cast<uintptr_t>(d_cmd) & 15))
+    return fail(GO2P_ERR_INVALID, "d_cmd must be 16-byte aligned");
   h->last_launches = 0;
-  if (B == 0) return GO2P_OK;
   DeviceGuard g(h->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MotorCmdDev* cmd = reinterpret_cast<MotorCmdDev*>(d_cmd);
   switch (precision) {
-    case GO2P_PREC_FP32: return launch_fp32(h, d_obs, d_button0, d_act, d_qdes, B, flags, st);
+    case GO2P_PREC_FP32: return launch_fp32(h, d_obs, d_button0, d_act, d_qdes, cmd, B, flags, st);
     case GO2P_PREC_BF16:
     case GO2P_PREC_FP16:
-      if (h->tc_ok) return launch_tc(h, d_obs, d_button0, d_act, d_qdes, B, precision == GO2P_PREC_FP16, flags, st);
+      if (h->tc_ok) return launch_tc(h, d_obs, d_button0, d_act, d_qdes, cmd, B, precision == GO2P_PREC_FP16, flags, st);
       if (h->wide_ok) {
-        int rc = wide_launch(h->wide, d_obs, d_button0, d_act, d_qdes, B, precision == GO2P_PREC_FP16, flags, h->cc,
+        int rc = wide_launch(h->wide, d_obs, d_button0, d_act, d_qdes, cmd, B, precision == GO2P_PREC_FP16, flags, h->cc,
                              h->sm_count, st, &h->last_launches, g_err, h->scratch_sel);
         return rc ? fail(rc, g_err.c_str()) : GO2P_OK;
       }
       return fail(GO2P_ERR_UNSUPPORTED, "tensor-core kernels do not serve this layer shape; use GO2P_PREC_FP32");
-    case GO2P_PREC_TF32:
-      return fail(GO2P_ERR_UNSUPPORTED,
-                  "kind::tf32 is not built: fp32 weights of the policy do not fit beside the observation ring in "
-                  "shared memory; GO2P_PREC_FP16 has the same 11-bit significand");
     default: return fail(GO2P_ERR_INVALID, "unknown precision");
   }
 }
 
+int go2p_infer_batch_ex(go2p_handle* h, const float* d_obs, const int32_t* d_button0, float* d_act, double* d_qdes,
+                        int64_t B, int precision, uint32_t flags, void* stream) {
+  if (flags & GO2P_F_MOTOR_CMD) return fail(GO2P_ERR_INVALID, "GO2P_F_MOTOR_CMD needs go2p_infer_batch_cmd");
+  return go2p_infer_batch_cmd(h, d_obs, d_button0, d_act, d_qdes, nullptr, B, precision, flags, stream);
+}
+
 int go2p_infer_batch(go2p_handle* h, const float* d_obs, float* d_act, int64_t B, int precision, void* stream) {
-  return go2p_infer_batch_ex(h, d_obs, nullptr, d_act, nullptr, B, precision, 0u, stream);
+  return go2p_infer_batch_cmd(h, d_obs, nullptr, d_act, nullptr, nullptr, B, precision, 0u, stream);
 }
 
 int go2p_last_launch_count(const go2p_handle* h) { return h ? h->last_launches : 0; }
+
+// Isaac joint index of every Unitree motor (controller.hpp:168-170 vs the SDK's FR, FL, RR, RL x hip, thigh, calf)
+int go2p_motor_order(int32_t isaac_of_motor[GO2P_DOF]) {
+  if (!isaac_of_motor) return fail(GO2P_ERR_INVALID, "null argument");
+  for (int i = 0; i < GO2P_DOF; ++i) isaac_of_motor[motor_of_isaac(i)] = i;
+  return GO2P_OK;
+}
 
 int go2p_infer_batch_host(go2p_handle* h, const float* h_obs, float* h_act, int64_t B, int precision) {
   if (!h || !h_obs || !h_act) return fail(GO2P_ERR_INVALID, "go2p_infer_batch_host: null argument");
@@ -898,12 +985,14 @@ int go2p_infer_batch_host(go2p_handle* h, const float* h_obs, float* h_act, int6
   }
   int launches = 0;
   int slot = 0;
+  // Not re-entrant: one host thread per handle (the reference's single-threaded executor, controller.cpp:282);
+  // scratch_sel routes every stream of the pipeline to its own activation scratch.
   for (int64_t r0 = 0; r0 < B; r0 += chunk, slot = (slot + 1) % kPipeDepth) {
     const int64_t rows = std::min(chunk, B - r0);
     cudaStream_t st = h->pipe_stream[slot];
     CU_TRY(cudaMemcpyAsync(h->pipe_in[slot], h_obs + r0 * in, (size_t)rows * in * sizeof(float), cudaMemcpyHostToDevice, st));
     h->scratch_sel = 1 + slot;
-    int rc = go2p_infer_batch_ex(h, h->pipe_in[slot], nullptr, h->pipe_out[slot], nullptr, rows, precision, 0u, st);
+    int rc = go2p_infer_batch_cmd(h, h->pipe_in[slot], nullptr, h->pipe_out[slot], nullptr, nullptr, rows, precision, 0u, st);
     h->scratch_sel = 0;
     if (rc) return rc;
     launches += h->last_launches;
@@ -926,29 +1015,207 @@ int go2p_assemble_batch(go2p_handle* h, const go2p_raw_state* d_raw, const float
   return GO2P_OK;
 }
 
-int go2p_step_batch(go2p_handle* h, const go2p_raw_state* d_raw, float* d_vel_cmd, float* d_obs, float* d_action,
-                    double* d_qdes, int64_t B, int precision, void* stream) {
-  if (!h || !d_raw || !d_vel_cmd || !d_obs || !d_action || !d_qdes)
+namespace {
+// publish() for B robots on device buffers; button_scratch [B] receives the dead-man buttons for the epilogue
+int step_batch_on(go2p_handle* h, const go2p_raw_state* d_raw, float* d_vel_cmd, float* d_obs, float* d_action, double* d_qdes,
+                  go2p_motor_cmd* d_cmd, int32_t* button_scratch, int64_t B, int precision, cudaStream_t st) {
+  // A1-A6: d_action still holds the previous published action here
+  launch_assemble_batch(reinterpret_cast<const RawStateDev*>(d_raw), d_action, d_vel_cmd, d_obs, B, h->cc, button_scratch,
+                        h->sm_count, st);
+  CU_TRY(cudaGetLastError());
+  // A7 + A9 + A11
+  const uint32_t flags = GO2P_F_CLAMP_MASK | (d_qdes ? GO2P_F_QDES : 0u) | (d_cmd ? GO2P_F_MOTOR_CMD : 0u);
+  const int rc = go2p_infer_batch_cmd(h, d_obs, button_scratch, d_action, d_qdes, d_cmd, B, precision, flags, st);
+  if (rc == GO2P_OK) h->last_launches += 1;
+  return rc;
+}
+}  // namespace
+
+int go2p_step_batch_cmd(go2p_handle* h, const go2p_raw_state* d_raw, float* d_vel_cmd, float* d_obs, float* d_action,
+                        double* d_qdes, go2p_motor_cmd* d_cmd, int64_t B, int precision, void* stream) {
+  if (!h || !d_raw || !d_vel_cmd || !d_obs || !d_action || (!d_qdes && !d_cmd))
     return fail(GO2P_ERR_INVALID, "go2p_step_batch: null argument");
   if (B <= 0) return B == 0 ? GO2P_OK : fail(GO2P_ERR_INVALID, "negative batch");
   if (h->dm.in_dim != kFrame * h->cc.H || h->dm.out_dim != kDof)
     return fail(GO2P_ERR_INVALID, "go2p_step_batch: the policy is not a 49*H -> 12 controller policy");
   DeviceGuard g(h->device);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (h->step_button_rows < B) {
     if (h->d_step_button) { h->dev_owned.push_back(h->d_step_button); h->d_step_button = nullptr; }   // retired, see ensure_scratch
     CU_TRY(cudaMalloc((void**)&h->d_step_button, (size_t)B * sizeof(int32_t)));
     h->step_button_rows = B;
   }
-  // A1-A6: d_action still holds the previous published action here
-  launch_assemble_batch(reinterpret_cast<const RawStateDev*>(d_raw), d_action, d_vel_cmd, d_obs, B, h->cc, h->d_step_button,
-                        h->sm_count, st);
-  CU_TRY(cudaGetLastError());
-  // A7 + A9 + A11
-  const int rc = go2p_infer_batch_ex(h, d_obs, h->d_step_button, d_action, d_qdes, B, precision,
-                                     GO2P_F_CLAMP_MASK | GO2P_F_QDES, stream);
-  if (rc == GO2P_OK) h->last_launches += 1;
-  return rc;
+  return step_batch_on(h, d_raw, d_vel_cmd, d_obs, d_action, d_qdes, d_cmd, h->d_step_button, B, precision,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int go2p_step_batch(go2p_handle* h, const go2p_raw_state* d_raw, float* d_vel_cmd, float* d_obs, float* d_action,
+                    double* d_qdes, int64_t B, int precision, void* stream) {
+  if (!d_qdes) return fail(GO2P_ERR_INVALID, "go2p_step_batch: null argument");
+  return go2p_step_batch_cmd(h, d_raw, d_vel_cmd, d_obs, d_action, d_qdes, nullptr, B, precision, stream);
+}
+
+// Closed-loop control step for a fleet from HOST buffers: per-robot history / joystick command / previous action stay
+// on the device inside the handle, so a step moves 156 B of raw state in and 48 B of action (+ 112 B of motor command
+// if asked for) out per robot instead of the 392 + 48 B of go2p_infer_batch_host.
+int go2p_step_batch_host(go2p_handle* h, const go2p_raw_state* h_raw, float* h_action, go2p_motor_cmd* h_cmd, int64_t B,
+                         int precision) {
+  if (!h || !h_raw || !h_action) return fail(GO2P_ERR_INVALID, "go2p_step_batch_host: null argument");
+  if (B <= 0) return B == 0 ? GO2P_OK : fail(GO2P_ERR_INVALID, "negative batch");
+  if (h->dm.in_dim != kFrame * h->cc.H || h->dm.out_dim != kDof)
+    return fail(GO2P_ERR_INVALID, "go2p_step_batch_host: the policy is not a 49*H -> 12 controller policy");
+  DeviceGuard g(h->device);
+  go2p_handle::Fleet& f = h->fleet;
+  const int n_obs = h->dm.in_dim;
+  if (f.robots != B) {
+    // (re)create the fleet state: histories 0, joystick command 0, previous action 0 (controller.hpp:132-162)
+    for (void* p : {(void*)f.obs, (void*)f.vel, (void*)f.act}) if (p) h->dev_owned.push_back(p);
+    f.obs = f.vel = f.act = nullptr;
+    CU_TRY(cudaMalloc((void**)&f.obs, (size_t)B * n_obs * sizeof(float)));
+    CU_TRY(cudaMalloc((void**)&f.vel, (size_t)B * 3 * sizeof(float)));
+    CU_TRY(cudaMalloc((void**)&f.act, (size_t)B * kDof * sizeof(float)));
+    CU_TRY(cudaMemsetAsync(f.obs, 0, (size_t)B * n_obs * sizeof(float), h->pipe_stream[0]));
+    CU_TRY(cudaMemsetAsync(f.vel, 0, (size_t)B * 3 * sizeof(float), h->pipe_stream[0]));
+    CU_TRY(cudaMemsetAsync(f.act, 0, (size_t)B * kDof * sizeof(float), h->pipe_stream[0]));
+    CU_TRY(cudaStreamSynchronize(h->pipe_stream[0]));
+    f.robots = B;
+  }
+  for (int i = 0; i < kPipeDepth; ++i) {
+    if (!f.raw[i]) {
+      CU_TRY(cudaMalloc((void**)&f.raw[i], (size_t)kHostChunkRows * sizeof(go2p_raw_state)));
+      CU_TRY(cudaMalloc((void**)&f.cmd[i], (size_t)kHostChunkRows * sizeof(MotorCmdDev)));
+      CU_TRY(cudaMalloc((void**)&f.button[i], (size_t)kHostChunkRows * sizeof(int32_t)));
+    }
+  }
+  const int64_t chunk = std::min<int64_t>(B, kHostChunkRows);
+  int launches = 0, slot = 0;
+  for (int64_t r0 = 0; r0 < B; r0 += chunk, slot = (slot + 1) % kPipeDepth) {
+    const int64_t rows = std::min(chunk, B - r0);
+    cudaStream_t st = h->pipe_stream[slot];
+    CU_TRY(cudaMemcpyAsync(f.raw[slot], h_raw + r0, (size_t)rows * sizeof(go2p_raw_state), cudaMemcpyHostToDevice, st));
+    h->scratch_sel = 1 + slot;
+    int rc = step_batch_on(h, f.raw[slot], f.vel + r0 * 3, f.obs + r0 * n_obs, f.act + r0 * kDof, nullptr,
+                           h_cmd ? reinterpret_cast<go2p_motor_cmd*>(f.cmd[slot]) : nullptr, f.button[slot], rows, precision, st);
+    h->scratch_sel = 0;
+    if (rc) return rc;
+    launches += h->last_launches;
+    CU_TRY(cudaMemcpyAsync(h_action + r0 * kDof, f.act + r0 * kDof, (size_t)rows * kDof * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (h_cmd) CU_TRY(cudaMemcpyAsync(h_cmd + r0, f.cmd[slot], (size_t)rows * sizeof(MotorCmdDev), cudaMemcpyDeviceToHost, st));
+  }
+  for (int i = 0; i < kPipeDepth; ++i) CU_TRY(cudaStreamSynchronize(h->pipe_stream[i]));
+  h->last_launches = launches;
+  return GO2P_OK;
+}
+
+int go2p_step_batch_host_reset(go2p_handle* h) {
+  if (!h) return fail(GO2P_ERR_INVALID, "null handle");
+  h->fleet.robots = 0;     // the next go2p_step_batch_host call re-creates zeroed state
+  return GO2P_OK;
+}
+
+// ------------------------------------------------------------------------------------- ObservationAction log
+int go2p_log_enable(go2p_handle* h, int capacity) {
+  if (!h || capacity < 0) return fail(GO2P_ERR_INVALID, "go2p_log_enable: bad argument");
+  DeviceGuard g(h->device);
+  const bool was_resident = h->resident;
+  if (was_resident) { int rc = go2p_persistent_stop(h); if (rc) return rc; }   // the ring pointer is a launch argument
+  if (h->d_log) { cudaFree(h->d_log); h->d_log = nullptr; }
+  h->log_capacity = 0; h->log_tail = 0;
+  if (capacity > 0) {
+    const size_t bytes = sizeof(LogRing) + (size_t)capacity * kLogRecFloats * sizeof(float);
+    CU_TRY(cudaMalloc((void**)&h->d_log, bytes));
+    CU_TRY(cudaMemset(h->d_log, 0, bytes));
+    LogRing hdr{};
+    hdr.head = 0; hdr.capacity = (uint32_t)capacity; hdr.n_obs = (uint32_t)h->dm.in_dim;
+    CU_TRY(cudaMemcpy(h->d_log, &hdr, offsetof(LogRing, rec), cudaMemcpyHostToDevice));
+    h->log_capacity = (uint32_t)capacity;
+  }
+  if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }   // captured arguments are stale
+  if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
+  if (was_resident) return go2p_persistent_start(h);
+  return GO2P_OK;
+}
+
+int go2p_log_drain(go2p_handle* h, float* out, int max_records, int* n_records, uint64_t* dropped) {
+  if (!h || !out || !n_records || max_records < 0) return fail(GO2P_ERR_INVALID, "go2p_log_drain: bad argument");
+  *n_records = 0;
+  if (dropped) *dropped = 0;
+  if (!h->d_log) return fail(GO2P_ERR_STATE, "go2p_log_drain: logging is off (go2p_log_enable)");
+  DeviceGuard g(h->device);
+  cudaStream_t st = h->pipe_stream[0];      // a copy stream: works while the resident kernel runs
+  unsigned long long head = 0;
+  CU_TRY(cudaMemcpyAsync(&head, &h->d_log->head, sizeof(head), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  uint64_t tail = h->log_tail;
+  if (head - tail > h->log_capacity) {      // the writer lapped the reader: the oldest records are gone
+    if (dropped) *dropped = head - tail - h->log_capacity;
+    tail = head - h->log_capacity;
+  }
+  const int n = (int)std::min<uint64_t>(head - tail, (uint64_t)max_records);
+  const size_t rec_floats = (size_t)h->dm.in_dim + kDof;        // the message payload: float32[n_obs] + float32[12]
+  for (int done = 0; done < n;) {
+    const uint64_t idx = (tail + done) % h->log_capacity;
+    const int run = (int)std::min<uint64_t>((uint64_t)(n - done), h->log_capacity - idx);
+    CU_TRY(cudaMemcpy2DAsync(out + (size_t)done * rec_floats, rec_floats * sizeof(float),
+                             h->d_log->rec + idx * kLogRecFloats, (size_t)kLogRecFloats * sizeof(float),
+                             rec_floats * sizeof(float), (size_t)run, cudaMemcpyDeviceToHost, st));
+    done += run;
+  }
+  CU_TRY(cudaStreamSynchronize(st));
+  h->log_tail = tail + n;
+  *n_records = n;
+  return GO2P_OK;
+}
+
+// ------------------------------------------------------------------------------------- several GPUs, one process
+int go2p_shard_rows(int64_t B, int n, int i, int64_t* begin, int64_t* end) {
+  if (B < 0 || n < 1 || i < 0 || i >= n || !begin || !end) return fail(GO2P_ERR_INVALID, "go2p_shard_rows: bad argument");
+  const int64_t q = B / n, r = B % n;
+  *begin = i * q + std::min<int64_t>(i, r);
+  *end = *begin + q + (i < r ? 1 : 0);
+  return GO2P_OK;
+}
+
+int go2p_fleet_create(const char* onnx_path, const go2p_config* cfg_in, const int32_t* devices, int n_devices, go2p_fleet** out) {
+  if (!onnx_path || !devices || n_devices < 1 || !out) return fail(GO2P_ERR_INVALID, "go2p_fleet_create: bad argument");
+  *out = nullptr;
+  auto* f = new go2p_fleet();
+  for (int i = 0; i < n_devices; ++i) {
+    go2p_config cfg;
+    if (cfg_in) cfg = *cfg_in; else go2p_config_default(&cfg);
+    cfg.device = devices[i];
+    go2p_handle* h = nullptr;
+    const int rc = go2p_create(onnx_path, &cfg, &h);
+    if (rc) { const std::string keep = g_err; go2p_fleet_destroy(f); g_err = keep; return rc; }
+    f->handles.push_back(h);
+  }
+  *out = f;
+  return GO2P_OK;
+}
+
+int go2p_fleet_destroy(go2p_fleet* f) {
+  if (!f) return GO2P_OK;
+  for (go2p_handle* h : f->handles) go2p_destroy(h);
+  delete f;
+  return GO2P_OK;
+}
+
+int go2p_fleet_device_count(const go2p_fleet* f) { return f ? (int)f->handles.size() : 0; }
+
+
+int go2p_fleet_infer_host(go2p_fleet* f, const float* h_obs, float* h_act, int64_t B, int precision) {
+  if (!f || f->handles.empty() || !h_obs || !h_act || B < 0) return fail(GO2P_ERR_INVALID, "go2p_fleet_infer_host: bad argument");
+  const int in = f->handles[0]->dm.in_dim, out = f->handles[0]->dm.out_dim;
+  return fleet_run(f, B, [&](go2p_handle* h, int64_t r0, int64_t rows) {
+    return go2p_infer_batch_host(h, h_obs + r0 * in, h_act + r0 * out, rows, precision);
+  });
+}
+
+int go2p_fleet_step_host(go2p_fleet* f, const go2p_raw_state* h_raw, float* h_action, go2p_motor_cmd* h_cmd, int64_t B,
+                         int precision) {
+  if (!f || f->handles.empty() || !h_raw || !h_action || B < 0) return fail(GO2P_ERR_INVALID, "go2p_fleet_step_host: bad argument");
+  return fleet_run(f, B, [&](go2p_handle* h, int64_t r0, int64_t rows) {
+    return go2p_step_batch_host(h, h_raw + r0, h_action + r0 * kDof, h_cmd ? h_cmd + r0 : nullptr, rows, precision);
+  });
 }
 
 // ------------------------------------------------------------------------------------- helpers

@@ -34,6 +34,17 @@ struct B1State {
   uint32_t pad;
 };
 
+// ObservationAction log (reference: onnx_interfaces/msg/ObservationAction.msg:1-2, filled at controller.cpp:226-229):
+// one record per control step = the observation as fed to the policy + the published action, appended to a ring in
+// device memory by the step that produced it; `head` counts records ever written and is stored (release) after the
+// record, so a drain that reads head and then the records sees complete records only.
+constexpr int kLogRecFloats = kFrame * kMaxHistory + kDof;   // fixed pitch: 49*8 + 12 floats
+struct LogRing {
+  unsigned long long head;
+  uint32_t capacity, n_obs;
+  float rec[1];            // [capacity][kLogRecFloats]
+};
+
 struct B1Args {
   DevModel model;
   CtrlConst cc;
@@ -48,6 +59,7 @@ struct B1Args {
   // abandoned handle can never pin an SM (or hang a GPU box) for longer than this.
   unsigned long long idle_ns;
   uint32_t epoch;
+  LogRing* log;             // ObservationAction ring in device memory, or null (logging off: no HBM traffic per step)
 };
 constexpr int kOutSlots = 1024;
 constexpr int kByeSlot = kOutSlots - 1;
@@ -534,6 +546,17 @@ __global__ void __launch_bounds__(kB1Threads, 1) b1_kernel(const B1Args a) {
     }
     if (tid == 0) st->seq = want;
     block_sync();
+    if (type == MSG_STEP && a.log) {
+      // ObservationAction record of this step (controller.cpp:226-229): the observation as fed + the published action
+      LogRing* lg = a.log;
+      const unsigned long long head = lg->head;      // only this CTA writes it
+      float* rec = lg->rec + (size_t)(head % lg->capacity) * kLogRecFloats;
+      if (tid < n_obs) rec[tid] = st->obs[tid];
+      if (tid >= 416 && tid < 416 + kDof) rec[n_obs + tid - 416] = st->action[tid - 416];
+      __threadfence();
+      block_sync();
+      if (tid == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&lg->head), "l"(head + 1ull) : "memory");
+    }
     if (!kResident) return;
   }
 }

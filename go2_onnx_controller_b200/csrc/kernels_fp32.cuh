@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kSoRows, 1)
 small_out_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Wrm, int Kp,
                  const float* __restrict__ bias, float* __restrict__ C, int ldc, long long M, int K, int N,
                  int has_elu, float alpha, uint32_t flags, const int32_t* __restrict__ button0,
-                 double* __restrict__ qdes, CtrlConst cc) {
+                 double* __restrict__ qdes, MotorCmdDev* __restrict__ cmd, CtrlConst cc) {
   extern __shared__ __align__(16) float so_sm[];
   const int pitch = K | 1;
   float* As = so_sm;                       // [128][pitch]
@@ -138,7 +138,8 @@ small_out_kernel(const float* __restrict__ A, int lda, const float* __restrict__
       if (n < N) acc[n] = fmaf(xv, Ws[n * Kp + k], acc[n]);
   }
   const long long row = row0 + tid;
-  const int b0 = (button0 && (flags & 1u)) ? button0[row] : 0;
+  const int b0 = (button0 && (flags & 5u)) ? button0[row] : 0;
+  if ((flags & 4u) && cmd) store_gains(cmd, row, b0, cc.kp, cc.kd, cc.kp_deadman);
 #pragma unroll
   for (int n = 0; n < 32; ++n) {
     if (n >= N) break;
@@ -146,20 +147,31 @@ small_out_kernel(const float* __restrict__ A, int lda, const float* __restrict__
     if (has_elu) v = elu_exact(v, alpha);
     if (flags & 1u) v = clamp_mask(v, cc.action_limit, b0);
     C[(size_t)row * ldc + n] = v;
-    if ((flags & 2u) && qdes && n < kDof) qdes[(size_t)row * kDof + n] = joint_target(v, cc.q0[n], cc.action_scale);
+    if (n < kDof && (flags & 6u)) {
+      const double qd = joint_target(v, cc.q0[n], cc.action_scale);
+      if ((flags & 2u) && qdes) qdes[(size_t)row * kDof + n] = qd;
+      if ((flags & 4u) && cmd) cmd[row].q_des[motor_of_isaac(n)] = qd;
+    }
   }
 }
 
 // Elementwise A9/A11 for models whose output layer is too wide for small_out_kernel.
 __global__ void post_kernel(float* __restrict__ act, long long total, int out_dim, uint32_t flags,
-                            const int32_t* __restrict__ button0, double* __restrict__ qdes, const __grid_constant__ CtrlConst cc) {
+                            const int32_t* __restrict__ button0, double* __restrict__ qdes, MotorCmdDev* __restrict__ cmd,
+                            const __grid_constant__ CtrlConst cc) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const long long row = i / out_dim;
   const int n = (int)(i - row * out_dim);
+  const int b0 = ((flags & 5u) && button0) ? button0[row] : 0;
   float v = act[i];
-  if (flags & 1u) { v = clamp_mask(v, cc.action_limit, button0 ? button0[row] : 0); act[i] = v; }
-  if ((flags & 2u) && qdes && n < kDof) qdes[row * kDof + n] = joint_target(v, cc.q0[n], cc.action_scale);
+  if (flags & 1u) { v = clamp_mask(v, cc.action_limit, b0); act[i] = v; }
+  if (n < kDof && (flags & 6u)) {
+    const double qd = joint_target(v, cc.q0[n], cc.action_scale);
+    if ((flags & 2u) && qdes) qdes[row * kDof + n] = qd;
+    if ((flags & 4u) && cmd) cmd[row].q_des[motor_of_isaac(n)] = qd;
+  }
+  if (n == 0 && (flags & 4u) && cmd) store_gains(cmd, row, b0, cc.kp, cc.kd, cc.kp_deadman);
 }
 
 // A1-A6 for B robots: one thread per observation element, history kept in the obs rows themselves

@@ -59,6 +59,8 @@ struct TcArgs {
   float action_limit;
   double action_scale;
   double q0[kDof];
+  MotorCmdDev* cmd;          // [B] send_command arguments in Unitree motor order (flag 4) or null
+  float kp, kd, kp_deadman;
   unsigned long long* trace;   // debug timeline (GO2P_TC_TRACE): [0] = count, then (event, clock64) pairs; CTA 0 only
 };
 
@@ -177,7 +179,7 @@ __device__ __noinline__ void tc_out_generic(const TcArgs& a, uint32_t o_t, long 
   ptx::tc_wait_ld();
   if (!live) return;
   const int L = a.n_layers - 1;
-  const int b0 = (a.flags & 1u) && a.button0 ? a.button0[row] : 0;
+  const int b0 = (a.flags & 5u) && a.button0 ? a.button0[row] : 0;
   float* dst = a.act + row * a.out_dim;
 #pragma unroll 1
   for (int j = 0; j < a.out_dim; ++j) {
@@ -187,8 +189,13 @@ __device__ __noinline__ void tc_out_generic(const TcArgs& a, uint32_t o_t, long 
     if (a.has_elu[L]) x = ((x < 0.f) ? fmaf(ptx::ex2_approx(x), a.elu_c[L], -a.elu_c[L]) : x) * a.out_scale;
     if (a.flags & 1u) x = clamp_mask(x, a.action_limit, b0);
     dst[j] = x;
-    if ((a.flags & 2u) && a.qdes && j < kDof) a.qdes[row * kDof + j] = joint_target(x, a.q0[j], a.action_scale);
+    if (j < kDof && (a.flags & 6u)) {
+      const double qd = joint_target(x, a.q0[j], a.action_scale);
+      if ((a.flags & 2u) && a.qdes) a.qdes[row * kDof + j] = qd;
+      if ((a.flags & 4u) && a.cmd) a.cmd[row].q_des[motor_of_isaac(j)] = qd;
+    }
   }
+  if ((a.flags & 4u) && a.cmd) store_gains(a.cmd, row, b0, a.kp, a.kd, a.kp_deadman);
 }
 
 template <bool kFp16>
@@ -330,7 +337,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
     const bool even = (a.in_dim & 1) == 0;
 
     uint32_t par_acc[2] = {0u, 0u};
-    const bool masked = (a.flags & 1u) && a.button0 != nullptr;
+    const bool masked = (a.flags & 5u) && a.button0 != nullptr;   // the clamp/mask and the kp selection read the button
     int b0_s0 = 0, b0_s1 = 0;                // dead-man buttons of this thread's row in the two slots' tiles
     // ---- conv(s): fp32 observation rows -> 16-bit layer-0 A operand, constant ones at K = in_dim, in_dim+1.
     //      chunk c8 (16 K elements = 8 columns) lands at 32*(c8/2) + 8*(c8%2) of buffer phi: block cb = chunks 2cb, 2cb+1
@@ -401,10 +408,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
               for (int j = 0; j < 4; ++j) o[j] = clamp_mask(o[j], a.action_limit, b0);
             }
             reinterpret_cast<float4*>(a.act + row * 12)[cb] = make_float4(o[0], o[1], o[2], o[3]);
-            if ((a.flags & 2u) && a.qdes) {
-              double2* q2 = reinterpret_cast<double2*>(a.qdes + row * kDof + cb * 4);
-              q2[0] = make_double2(joint_target(o[0], a.q0[cb * 4 + 0], a.action_scale), joint_target(o[1], a.q0[cb * 4 + 1], a.action_scale));
-              q2[1] = make_double2(joint_target(o[2], a.q0[cb * 4 + 2], a.action_scale), joint_target(o[3], a.q0[cb * 4 + 3], a.action_scale));
+            if (a.flags & 6u) {
+              double qd[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) qd[j] = joint_target(o[j], a.q0[cb * 4 + j], a.action_scale);
+              if ((a.flags & 2u) && a.qdes) {
+                double2* q2 = reinterpret_cast<double2*>(a.qdes + row * kDof + cb * 4);
+                q2[0] = make_double2(qd[0], qd[1]);
+                q2[1] = make_double2(qd[2], qd[3]);
+              }
+              if ((a.flags & 4u) && a.cmd) {
+                // Isaac joint 4*cb + j = joint type cb of leg j -> Unitree motor (j ^ 1)*3 + cb
+                MotorCmdDev* c = a.cmd + row;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) c->q_des[(j ^ 1) * 3 + cb] = qd[j];
+                if (cb == 0) store_gains(a.cmd, row, s ? b0_s1 : b0_s0, a.kp, a.kd, a.kp_deadman);
+              }
             }
           }
         }

@@ -83,6 +83,8 @@ struct WideGemmArgs {
   float* out_rows;          // [M, out_dim] fp32 (output layer)
   const int32_t* button0;
   double* qdes;
+  MotorCmdDev* cmd;         // send_command arguments in Unitree motor order (flag 4) or null
+  float kp, kd, kp_deadman;
   long long M;              // valid rows
   int m_tiles, n_tiles, k_chunks;
   int N, out_dim, has_elu;
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemm
         ptx::tmem_ld_x16(acc_t, v);
         ptx::tc_wait_ld();
         if (row < a.M && half == 0) {
-          const int b0 = ((a.flags & 1u) && a.button0) ? a.button0[row] : 0;
+          const int b0 = ((a.flags & 5u) && a.button0) ? a.button0[row] : 0;
           float* dst = a.out_rows + row * a.out_dim;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -308,9 +310,14 @@ __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemm
               if (a.has_elu) x = (x < 0.f) ? fmaf(a.alpha, ptx::ex2_approx(x * 1.4426950408889634f), -a.alpha) : x;
               if (a.flags & 1u) x = clamp_mask(x, a.action_limit, b0);
               dst[j] = x;
-              if ((a.flags & 2u) && a.qdes && j < kDof) a.qdes[row * kDof + j] = joint_target(x, a.q0[j], a.action_scale);
+              if (j < kDof && (a.flags & 6u)) {
+                const double qd = joint_target(x, a.q0[j], a.action_scale);
+                if ((a.flags & 2u) && a.qdes) a.qdes[row * kDof + j] = qd;
+                if ((a.flags & 4u) && a.cmd) a.cmd[row].q_des[motor_of_isaac(j)] = qd;
+              }
             }
           }
+          if ((a.flags & 4u) && a.cmd) store_gains(a.cmd, row, b0, a.kp, a.kd, a.kp_deadman);
         }
       }
       ptx::tc_fence_before();
@@ -449,7 +456,7 @@ inline void wide_release(WideModel* wm) {
 // activation (18944 x 1024 x 2 B = 39 MB) still stays in the 126 MB L2 together with the next layer's output
 constexpr long long kWdChunkRows = 148 * kWdTileM;
 
-inline int wide_launch(const WideModel& wm, const float* d_obs, const int32_t* d_button0, float* d_act, double* d_qdes, long long B,
+inline int wide_launch(const WideModel& wm, const float* d_obs, const int32_t* d_button0, float* d_act, double* d_qdes, MotorCmdDev* d_cmd, long long B,
                        bool fp16, uint32_t flags, const CtrlConst& cc, int sm_count, cudaStream_t st, int* launches, std::string& err, int set = 0) {
   if (set < 0 || set >= WideModel::kSets) { err = "wide_launch: bad stream set"; return 2; }
   uint16_t** act = wm.act[set];
@@ -484,6 +491,8 @@ inline int wide_launch(const WideModel& wm, const float* d_obs, const int32_t* d
       a.out_rows = last ? d_act + r0 * wm.out_dim : nullptr;
       a.button0 = d_button0 ? d_button0 + r0 : nullptr;
       a.qdes = d_qdes ? d_qdes + r0 * kDof : nullptr;
+      a.cmd = d_cmd ? d_cmd + r0 : nullptr;
+      a.kp = cc.kp; a.kd = cc.kd; a.kp_deadman = cc.kp_deadman;
       a.M = rows; a.m_tiles = m_tiles; a.n_tiles = L.Np / L.NT; a.k_chunks = L.Kp / kWdChunkK;
       a.N = L.N; a.out_dim = wm.out_dim; a.has_elu = L.has_elu; a.alpha = L.alpha;
       a.flags = last ? flags : 0u; a.action_limit = cc.action_limit; a.action_scale = cc.action_scale;

@@ -33,7 +33,19 @@ struct CtrlConst {
   float kp_deadman;
   int foot_threshold;
   int H;
+  float kp, kd;          // controller.hpp:119-120 (ROS parameters; go2p_set_gains)
 };
+
+// What Go2RobotInterface::send_command receives from publish() (controller.cpp:235-251), in UNITREE motor order:
+// motor u = leg_u*3 + joint with legs FR, FL, RR, RL and joints hip, thigh, calf, while the policy works in Isaac order
+// i = joint*4 + leg_i with legs FL, FR, RL, RR (controller.hpp:168-170) -- the same left/right swap as the foot
+// contacts (controller.hpp:100-103).  dq_des and tau_ff are zero in the reference and are not stored.
+struct MotorCmdDev {
+  double q_des[kDof];
+  double kp, kd;         // one value for all 12 joints (controller.cpp:246-247)
+};
+__host__ __device__ inline int motor_of_isaac(int i) { return (((i & 3) ^ 1) * 3) + (i >> 2); }
+
 
 // CTA barrier that is safe after thread-divergent code.  Measured on B200 (driver 580, CUDA 12.9): when nvcc
 // emits no reconvergence point between an `if (tid < n) {...}` and the following BAR.SYNC, a warp reaches the
@@ -55,6 +67,12 @@ __device__ __forceinline__ float clamp_mask(float a, float lim, int button0) {
 // q_des = q0 + (double)a * scale   (controller.cpp:244) -- no contraction into an FMA
 __device__ __forceinline__ double joint_target(float a, double q0, double scale) {
   return __dadd_rn(q0, __dmul_rn((double)a, scale));
+}
+
+// kp = button0 == 0 ? kp_ : 5, kd = kd_   (controller.cpp:246-247)
+__device__ __forceinline__ void store_gains(MotorCmdDev* cmd, long long row, int button0, float kp, float kd, float kp_deadman) {
+  cmd[row].kp = (double)((button0 == 0) ? kp : kp_deadman);
+  cmd[row].kd = (double)kd;
 }
 
 // ONNX Elu-6: x < 0 ? alpha*(exp(x)-1) : x ; NaN and -0.0 pass through

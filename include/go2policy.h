@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GO2P_ABI_VERSION 1
+#define GO2P_ABI_VERSION 2
 #define GO2P_DOF 12            /* reference: controller.hpp:13 kDimDOF   */
 #define GO2P_FRAME 49          /* reference: controller.hpp:14 kDimObs   */
 #define GO2P_MAX_HISTORY 8     /* reference uses kHistory = 2 (controller.hpp:15) */
@@ -52,8 +52,9 @@ typedef enum go2p_status {
 typedef enum go2p_precision {
   GO2P_PREC_FP32 = 0,        /* CUDA-core FFMA; agrees with ORT-CPU semantics to 1e-5 */
   GO2P_PREC_BF16 = 1,        /* tcgen05 kind::f16, bf16 operands                        */
-  GO2P_PREC_FP16 = 2,        /* tcgen05 kind::f16, fp16 operands (saturating convert)   */
-  GO2P_PREC_TF32 = 3         /* tcgen05 kind::tf32                                      */
+  GO2P_PREC_FP16 = 2         /* tcgen05 kind::f16, fp16 operands (saturating convert)   */
+  /* 3 was reserved for kind::tf32 and is rejected: fp32 weights of the policy do not fit in shared memory beside the
+   * observation ring, and fp16 operands have the same 11-bit significand (precision contract) */
 } go2p_precision;
 
 /* how the batch-1 control-loop step reaches the GPU */
@@ -66,6 +67,7 @@ typedef enum go2p_b1_mode {
 /* flags of go2p_infer_batch_ex */
 #define GO2P_F_CLAMP_MASK 1u   /* apply A9 (clamp to +-action_limit, multiply by button0==0) */
 #define GO2P_F_QDES 2u         /* also emit A11 q_des = q0 + (double)a * action_scale        */
+#define GO2P_F_MOTOR_CMD 4u    /* also emit the send_command arguments in Unitree motor order (go2p_motor_cmd) */
 
 /* Compile-time constants of the reference exposed as one POD; go2p_config_default()
  * fills in the reference's values. */
@@ -108,6 +110,14 @@ typedef struct go2p_step_out {
   double kp, kd;               /* controller.cpp:246-247 (same value for all 12 joints)       */
   uint64_t device_ns;          /* in-kernel time from inputs-seen to outputs-written          */
 } go2p_step_out;
+
+/* What Go2RobotInterface::send_command receives from publish() (controller.cpp:235-251), in UNITREE motor order:
+ * motor u = leg*3 + joint with legs FR, FL, RR, RL and joints hip, thigh, calf; the policy works in Isaac order
+ * (controller.hpp:168-170: joint*4 + leg with legs FL, FR, RL, RR).  dq_des and tau_ff are zero in the reference. */
+typedef struct go2p_motor_cmd {
+  double q_des[GO2P_DOF];      /* controller.cpp:244, permuted to motor order                  */
+  double kp, kd;               /* controller.cpp:246-247: one value for all 12 joints          */
+} go2p_motor_cmd;
 
 typedef struct go2p_model_info_t {
   int32_t in_dim, out_dim, n_layers;
@@ -193,8 +203,50 @@ int go2p_assemble_batch(go2p_handle* h, const go2p_raw_state* d_raw, const float
  * kp/kd are per-robot functions of button0 alone (controller.cpp:246) and stay with the caller. */
 int go2p_step_batch(go2p_handle* h, const go2p_raw_state* d_raw, float* d_vel_cmd, float* d_obs,
                     float* d_action, double* d_qdes, int64_t B, int precision, void* stream);
+/* + the send_command arguments in Unitree motor order: d_cmd [B] go2p_motor_cmd (flag GO2P_F_MOTOR_CMD).  kp follows
+ * d_button0 (controller.cpp:246) with the handle's gains (go2p_config.kp/kd, go2p_set_gains). */
+int go2p_infer_batch_cmd(go2p_handle* h, const float* d_obs, const int32_t* d_button0, float* d_act,
+                         double* d_qdes, go2p_motor_cmd* d_cmd, int64_t B, int precision,
+                         uint32_t flags, void* stream);
+/* go2p_step_batch ending in motor commands: d_qdes or d_cmd may be NULL, not both */
+int go2p_step_batch_cmd(go2p_handle* h, const go2p_raw_state* d_raw, float* d_vel_cmd, float* d_obs,
+                        float* d_action, double* d_qdes, go2p_motor_cmd* d_cmd, int64_t B,
+                        int precision, void* stream);
+/* go2p_step_fused + the same step's send_command arguments in motor order (out may be NULL) */
+int go2p_step_fused_cmd(go2p_handle* h, const go2p_raw_state* raw, go2p_step_out* out, go2p_motor_cmd* cmd);
+/* isaac_of_motor[u] = Isaac joint index of Unitree motor u */
+int go2p_motor_order(int32_t isaac_of_motor[GO2P_DOF]);
+/* Closed-loop control step for B robots from HOST buffers (pinned for full PCIe rate): the robots' observation
+ * history, joystick command and previous action live on the device inside the handle (zeroed when B changes or after
+ * go2p_step_batch_host_reset), so a step moves 156 B/robot in and 48 B/robot out (+112 B with h_cmd) instead of the
+ * 392 + 48 B of go2p_infer_batch_host.  h_action [B,12] out, h_cmd [B] out or NULL.  Synchronous. */
+int go2p_step_batch_host(go2p_handle* h, const go2p_raw_state* h_raw, float* h_action, go2p_motor_cmd* h_cmd,
+                         int64_t B, int precision);
+int go2p_step_batch_host_reset(go2p_handle* h);
 /* number of kernels the previous batched call launched (for bench.py's gpu_launches) */
 int go2p_last_launch_count(const go2p_handle* h);
+
+/* ---- ObservationAction log (reference: onnx_interfaces/msg/ObservationAction.msg:1-2, filled at
+ * controller.cpp:226-229): every go2p_step_fused appends float32[in_dim] observation + float32[12] published action to
+ * a ring of `capacity` records in device memory; go2p_log_drain copies the records written since the last drain,
+ * oldest first, tightly packed ((in_dim + 12) floats each), without stopping the resident kernel.  capacity 0 turns
+ * logging off (the default: a control step then touches no device memory at all). */
+int go2p_log_enable(go2p_handle* h, int capacity);
+int go2p_log_drain(go2p_handle* h, float* out, int max_records, int* n_records, uint64_t* dropped);
+
+/* ---- one process, several GPUs: the rows of a batch are split into contiguous shards, one per
+ * device, each served by its own handle, host thread and stream set; weights are replicated at create time and no
+ * data crosses between devices (no collective on this path). */
+typedef struct go2p_fleet go2p_fleet;
+int go2p_fleet_create(const char* onnx_path, const go2p_config* cfg, const int32_t* devices, int n_devices,
+                      go2p_fleet** out);
+int go2p_fleet_destroy(go2p_fleet* f);
+int go2p_fleet_device_count(const go2p_fleet* f);
+/* rows [begin, end) of a B-row batch that shard `i` of `n` serves (contiguous, sizes differ by at most one) */
+int go2p_shard_rows(int64_t B, int n, int i, int64_t* begin, int64_t* end);
+int go2p_fleet_infer_host(go2p_fleet* f, const float* h_obs, float* h_act, int64_t B, int precision);
+int go2p_fleet_step_host(go2p_fleet* f, const go2p_raw_state* h_raw, float* h_action, go2p_motor_cmd* h_cmd,
+                         int64_t B, int precision);
 
 /* ---- small device / pinned-memory helpers so non-CUDA hosts can drive the batched path ---- */
 int go2p_dev_alloc(go2p_handle* h, size_t bytes, void** dptr);

@@ -140,6 +140,19 @@ def joint_targets(action: np.ndarray, button0, kp=KP_DEFAULT, kd=KD_DEFAULT):
     return q_des, kp_eff, F64(F32(kd))
 
 
+# Isaac joint order (reference: controller.hpp:168-170, breadth-first: joint*4 + leg, legs FL FR RL RR) -> Unitree motor
+# order (SDK: leg*3 + joint, legs FR FL RR RL).  The permutation itself lives in the out-of-tree Go2RobotInterface
+# (README.md:5); it is the same left/right swap as the foot contacts, controller.hpp:100-103.
+ISAAC_JOINTS = [f"{leg}_{j}" for j in ("hip", "thigh", "calf") for leg in ("FL", "FR", "RL", "RR")]
+UNITREE_MOTORS = [f"{leg}_{j}" for leg in ("FR", "FL", "RR", "RL") for j in ("hip", "thigh", "calf")]
+ISAAC_OF_MOTOR = np.array([ISAAC_JOINTS.index(n) for n in UNITREE_MOTORS])
+
+
+def motor_command(q_des_isaac: np.ndarray, kp, kd):
+    """send_command arguments (controller.cpp:235-251) re-ordered for the motors: (q_des[..., 12] motor order, kp, kd)."""
+    return np.asarray(q_des_isaac)[..., ISAAC_OF_MOTOR], kp, kd
+
+
 # ----------------------------------------------------------------------------
 # A1-A6: observation assembly  (reference: controller.cpp:173-212)
 # ----------------------------------------------------------------------------

@@ -39,7 +39,7 @@ def test_header_symbols_all_exported(lib):
 
 
 def test_abi_version_and_config_defaults(lib):
-    assert lib.go2p_abi_version() == 1
+    assert lib.go2p_abi_version() == 2
     cfg = actor.default_config()
     # reference constants: controller.hpp:13-16,100-103,119-120,165; controller.cpp:244,246
     assert cfg.struct_size == C.sizeof(capi.Config)
@@ -52,6 +52,31 @@ def test_abi_version_and_config_defaults(lib):
 def test_struct_layouts_match_header():
     assert C.sizeof(capi.RawState) == 4 * 35 + 8 + 8
     assert C.sizeof(capi.StepOut) == 4 * (49 * 8) + 48 + 48 + 96 + 16 + 8
+    assert C.sizeof(capi.MotorCmd) == 8 * 12 + 16
+
+
+def test_motor_order_is_the_left_right_swap_of_the_foot_contacts(lib):
+    """Unitree motor u = leg*3 + joint (legs FR, FL, RR, RL) <- Isaac joint*4 + leg (legs FL, FR, RL, RR,
+    controller.hpp:168-170): the same [1,0,3,2] leg swap as the foot contacts (controller.hpp:100-103)."""
+    order = (C.c_int32 * 12)()
+    assert lib.go2p_motor_order(order) == capi.OK
+    isaac = ["FL_hip", "FR_hip", "RL_hip", "RR_hip", "FL_thigh", "FR_thigh", "RL_thigh", "RR_thigh",
+             "FL_calf", "FR_calf", "RL_calf", "RR_calf"]
+    unitree = [f"{leg}_{j}" for leg in ("FR", "FL", "RR", "RL") for j in ("hip", "thigh", "calf")]
+    assert [isaac[i] for i in order] == unitree
+    assert sorted(order) == list(range(12))
+
+
+def test_shard_rows_partition(lib):
+    for B, n in ((1_048_576, 8), (10, 3), (0, 4), (5, 8)):
+        prev = 0
+        for i in range(n):
+            b, e = actor.shard_rows(B, n, i)
+            assert b == prev and e >= b and (e - b) in (B // n, B // n + 1)
+            prev = e
+        assert prev == B
+    b, e = C.c_int64(), C.c_int64()
+    assert lib.go2p_shard_rows(10, 0, 0, C.byref(b), C.byref(e)) == capi.ERR_INVALID
 
 
 def _create(lib, path, cfg=None):

@@ -3,8 +3,8 @@
 
 Tolerances:
   fp32 path   |a-ref| <= 1e-5*max(|ref|,1) per element and row rel-L2 <= 1e-5      (ref = fp64 oracle)
-  fp16 TC     <= 1e-2 abs on realistic observations (D2), <= 3e-2 on N(0,1) (D1)
-  bf16 TC     <= 5e-2 abs on D2, <= 1e-1 on D1
+  fp16 TC     <= 1e-2 abs on realistic observations (D2) and on N(0,1) (D1)
+  bf16 TC     <= 3e-2 abs on D2, <= 7e-2 on D1
   clamp/mask/q_des/obs layout/history: bit-exact; gravity projection <= 1 ulp
 """
 import ctypes as C
@@ -20,7 +20,10 @@ from oracle import coracle, oracle
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 
 TOL_FP32 = 1e-5
-TC_TOL = {capi.PREC_FP16: {"d2": 1e-2, "d1": 3e-2}, capi.PREC_BF16: {"d2": 5e-2, "d1": 1e-1}}
+# north_star: "a stated per-action tolerance, e.g. 1e-2 abs on normalised actions".  fp16 operands meet 1e-2 on both
+# input sets (measured 1.9e-3 on D2, 6-8e-3 on D1); bf16 operands cannot (8-bit significand: 1.5e-2 / 4-5e-2 measured)
+# and are offered with their own stated bound
+TC_TOL = {capi.PREC_FP16: {"d2": 1e-2, "d1": 1e-2}, capi.PREC_BF16: {"d2": 3e-2, "d1": 7e-2}}
 
 
 def bits(a):
@@ -254,7 +257,8 @@ def test_batched_ragged_sizes(torch_cuda, pb, cmodel, prec, B):
     if prec == capi.PREC_FP32:
         assert_fp32_parity(y.astype(np.float64), ref)
     else:
-        assert np.abs(y - ref).max() <= TC_TOL[prec]["d1"]
+        # the maximum over up to 38k x 12 actions of N(0,1) inputs is a tail statistic: 1.5x the 512-row golden bound
+        assert np.abs(y - ref).max() <= 1.5 * TC_TOL[prec]["d1"]
 
 
 def test_batched_empty_is_noop(torch_cuda, pb):
@@ -559,7 +563,9 @@ def test_wide_policy_tensor_core_path(torch_cuda, wide_model_path, prec):
         p.close()
 
 
-def test_unsupported_precision_fails_loudly(torch_cuda, pb, golden):
-    with pytest.raises(capi.Go2PolicyError) as e:
-        run_batch(torch_cuda, pb, golden["kat_obs"], capi.PREC_TF32)
-    assert e.value.code == capi.ERR_UNSUPPORTED
+def test_unknown_precision_fails_loudly(torch_cuda, pb, golden):
+    """3 was reserved for kind::tf32, which is not built (include/go2policy.h): it is rejected, never approximated."""
+    for bad in (3, 7, -1):
+        with pytest.raises(capi.Go2PolicyError) as e:
+            run_batch(torch_cuda, pb, golden["kat_obs"], bad)
+        assert e.value.code == capi.ERR_INVALID

@@ -1,0 +1,237 @@
+"""GPU parity tests of the round-2 additions (run on a B200 with -m gpu), all through the C ABI:
+  * send_command arguments in Unitree motor order from every output epilogue   (controller.cpp:235-251)
+  * ObservationAction ring on the device                                       (ObservationAction.msg:1-2)
+  * closed-loop fleet step from host buffers, several handles / devices in one process
+The oracle (oracle/) is only the checker."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from go2_onnx_controller_b200 import Fleet, Go2Controller, PolicyBatch, capi
+from oracle import coracle, oracle
+
+from test_gpu_parity import bits, raw_struct
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+CMD_DT = np.dtype([("q_des", np.float64, 12), ("kp", np.float64), ("kd", np.float64)])
+
+
+def run_cmd(torch, pb, X, prec, button0, flags):
+    B = X.shape[0]
+    d_obs = torch.from_numpy(np.ascontiguousarray(X, np.float32)).cuda()
+    d_act = torch.zeros((B, pb.out_dim), device="cuda")
+    d_q = torch.zeros((B, 12), device="cuda", dtype=torch.float64)
+    d_cmd = torch.zeros((B, CMD_DT.itemsize), device="cuda", dtype=torch.uint8)
+    d_b = torch.from_numpy(np.ascontiguousarray(button0, np.int32)).cuda()
+    pb.infer_device(d_obs.data_ptr(), d_act.data_ptr(), B, prec, 0, d_b.data_ptr(), d_q.data_ptr(), flags, d_cmd.data_ptr())
+    torch.cuda.synchronize()
+    return d_act.cpu().numpy(), d_q.cpu().numpy(), d_cmd.cpu().numpy().view(CMD_DT).reshape(B)
+
+
+def check_cmd(act, qd, cmd, button0, kp=28.0, kd=0.5):
+    exp_q, exp_kp, exp_kd = oracle.joint_targets(act, button0[:, None], kp, kd)
+    assert np.array_equal(qd.view(np.uint64), exp_q.view(np.uint64))                       # A11 bit-exact given the action
+    mq, _, _ = oracle.motor_command(exp_q, None, None)
+    assert np.array_equal(cmd["q_des"].view(np.uint64), mq.view(np.uint64))                # same doubles, motor order
+    assert np.array_equal(cmd["kp"], np.where(button0 == 0, np.float64(np.float32(kp)), 5.0))
+    assert np.array_equal(cmd["kd"], np.full(len(button0), np.float64(np.float32(kd))))
+
+
+@pytest.mark.parametrize("prec", [capi.PREC_FP32, capi.PREC_FP16, capi.PREC_BF16])
+def test_motor_cmd_from_the_fused_epilogues(torch_cuda, model_path, golden, prec):
+    """Unitree-order q_des/kp/kd next to the Isaac-order q_des: identical doubles, permuted; kp follows button0."""
+    pb = PolicyBatch(model_path)
+    try:
+        rng = np.random.default_rng(3)
+        X = np.concatenate([golden["d3_obs"], oracle.make_obs_d1(1000, 98, seed=4)]).astype(np.float32)
+        b0 = (rng.random(X.shape[0]) < 0.2).astype(np.int32)
+        act, qd, cmd = run_cmd(torch_cuda, pb, X, prec, b0, capi.F_CLAMP_MASK | capi.F_QDES | capi.F_MOTOR_CMD)
+        fin = np.isfinite(act).all(axis=1)
+        check_cmd(act[fin], qd[fin], cmd[fin], b0[fin])
+        assert not act[b0 == 1][np.isfinite(act[b0 == 1])].any()
+        # gains changed at run time (ROS parameters, controller.cpp:254-277) reach the batched epilogue
+        capi.check(pb._hd.lib.go2p_set_gains(pb._hd.h, 31.5, 0.75))
+        act, qd, cmd = run_cmd(torch_cuda, pb, X[:300], prec, b0[:300], capi.F_CLAMP_MASK | capi.F_QDES | capi.F_MOTOR_CMD)
+        fin = np.isfinite(act).all(axis=1)
+        check_cmd(act[fin], qd[fin], cmd[fin], b0[:300][fin], 31.5, 0.75)
+        # motor command without the Isaac-order q_des and without the clamp
+        d = run_cmd(torch_cuda, pb, X[256:400], prec, b0[256:400], capi.F_MOTOR_CMD)
+        exp_q, _, _ = oracle.joint_targets(d[0], 0)
+        assert np.array_equal(d[2]["q_des"].view(np.uint64), oracle.motor_command(exp_q, 0, 0)[0].view(np.uint64))
+        assert np.array_equal(d[2]["kp"], np.where(b0[256:400] == 0, np.float64(np.float32(31.5)), 5.0))
+    finally:
+        pb.close()
+
+
+def test_motor_cmd_other_epilogues(torch_cuda, tmp_path, wide_model_path):
+    """generic tcgen05 output epilogue (activation on the last layer), the wide per-layer GEMM path, and the fp32
+    GEMM + elementwise A9/A11 kernel that serves last hidden layers too wide for the staged output kernel."""
+    from oracle import onnx_mini
+    rng = np.random.default_rng(11)
+    cases = []
+    dims = (64, 128, 12)
+    ws = [rng.normal(0, 1.0 / np.sqrt(k), (n, k)).astype(np.float32) for k, n in zip(dims[:-1], dims[1:])]
+    bs = [rng.normal(0, 0.2, n).astype(np.float32) for n in dims[1:]]
+    p1 = tmp_path / "act_last.onnx"
+    p1.write_bytes(onnx_mini.write_mlp_onnx(ws, bs, 1.0, final_activation=True))
+    cases.append((str(p1), 64, (capi.PREC_FP32, capi.PREC_FP16, capi.PREC_BF16)))
+    cases.append((wide_model_path, 245, (capi.PREC_FP32, capi.PREC_FP16)))
+    dims = (40, 640, 12)        # 128 staged rows of 640 floats do not fit in shared memory -> GEMM + post kernel
+    ws = [rng.normal(0, 1.0 / np.sqrt(k), (n, k)).astype(np.float32) for k, n in zip(dims[:-1], dims[1:])]
+    bs = [rng.normal(0, 0.2, n).astype(np.float32) for n in dims[1:]]
+    p3 = tmp_path / "wide_last.onnx"
+    p3.write_bytes(onnx_mini.write_mlp_onnx(ws, bs, 1.0))
+    cases.append((str(p3), 40, (capi.PREC_FP32,)))
+    for path, in_dim, precs in cases:
+        pb = PolicyBatch(path)
+        cm = coracle.CModel(path)
+        try:
+            X = rng.normal(0, 1, (333, in_dim)).astype(np.float32)
+            b0 = (rng.random(333) < 0.3).astype(np.int32)
+            for prec in precs:
+                act, qd, cmd = run_cmd(torch_cuda, pb, X, prec, b0, capi.F_CLAMP_MASK | capi.F_QDES | capi.F_MOTOR_CMD)
+                check_cmd(act, qd, cmd, b0)
+                if prec == capi.PREC_FP32:
+                    ref = oracle.clamp_mask(cm.forward_f64(X, 4).astype(np.float32), b0[:, None])
+                    assert (np.abs(act - ref) / np.maximum(1, np.abs(ref))).max() <= 1e-5
+        finally:
+            pb.close()
+
+
+def test_step_fused_cmd_and_observation_action_ring(torch_cuda, model_path, golden_loop):
+    """Every control step's ObservationAction record (ObservationAction.msg:1-2, controller.cpp:226-229) lands in the
+    device ring byte-equal to what go2p_step_out returned; the ring drops the oldest records when it is lapped."""
+    g = golden_loop
+    ctl = Go2Controller(model_path)
+    try:
+        ctl.log_enable(64)
+        outs = []
+        for i in range(40):
+            out, cmd = ctl.step_cmd(raw_struct(g, i))
+            q = np.frombuffer(out.q_des, np.float64, 12)
+            assert np.array_equal(np.frombuffer(cmd.q_des, np.float64, 12), q[oracle.ISAAC_OF_MOTOR])
+            assert cmd.kp == out.kp and cmd.kd == out.kd
+            outs.append((np.frombuffer(out.observation, np.float32, 98).copy(), np.frombuffer(out.action, np.float32, 12).copy()))
+        obs, act, dropped = ctl.log_drain(25)            # partial drain: the oldest 25
+        assert obs.shape == (25, 98) and dropped == 0
+        for k in range(25):
+            assert np.array_equal(bits(obs[k]), bits(outs[k][0])) and np.array_equal(bits(act[k]), bits(outs[k][1]))
+        obs, act, dropped = ctl.log_drain()
+        assert obs.shape[0] == 15 and dropped == 0
+        assert np.array_equal(bits(obs[-1]), bits(outs[39][0])) and np.array_equal(bits(act[-1]), bits(outs[39][1]))
+        for i in range(40, 140):                           # 100 more steps lap the 64-record ring
+            out = ctl.step(raw_struct(g, i))
+            outs.append((np.frombuffer(out.observation, np.float32, 98).copy(), np.frombuffer(out.action, np.float32, 12).copy()))
+        obs, act, dropped = ctl.log_drain()
+        assert obs.shape[0] == 64 and dropped == 36
+        for k in range(64):
+            assert np.array_equal(bits(obs[k]), bits(outs[76 + k][0])) and np.array_equal(bits(act[k]), bits(outs[76 + k][1]))
+        ctl.log_enable(0)                                  # off again: steps still work, drain is refused
+        ctl.step(raw_struct(g, 0))
+        with pytest.raises(capi.Go2PolicyError):
+            ctl.log_drain()
+    finally:
+        ctl.close()
+
+
+RAW_DT = np.dtype([("quat", np.float32, 4), ("gyro", np.float32, 3), ("q", np.float32, 12), ("dq", np.float32, 12),
+                   ("axes", np.float32, 4), ("foot_force", np.int16, 4), ("joy_valid", np.int32), ("button0", np.int32)])
+assert RAW_DT.itemsize == C.sizeof(capi.RawState)
+
+
+def _raw_bytes(g, idx, button=None):
+    """go2p_raw_state records of the golden raw states idx, as uint8 [n, 156] (vectorised: no per-robot ctypes)."""
+    idx = np.asarray(idx)
+    r = np.zeros(len(idx), RAW_DT)
+    for f in ("quat", "gyro", "q", "dq", "axes", "foot_force", "joy_valid", "button0"):
+        r[f] = g["raw_" + f][idx]
+    if button is not None:
+        r["button0"] = np.asarray(button).astype(np.int32)
+    return r.view(np.uint8).reshape(len(idx), RAW_DT.itemsize).copy()
+
+
+@pytest.mark.parametrize("prec", [capi.PREC_FP32, capi.PREC_FP16])
+def test_step_batch_host_matches_device_step(torch_cuda, model_path, golden_loop, prec):
+    """go2p_step_batch_host (raw states in, actions + motor commands out, history resident in the handle) against
+    go2p_step_batch_cmd on caller-owned device buffers: identical bits step after step, ragged chunking included."""
+    torch = torch_cuda
+    g = golden_loop
+    n_g = g["obs"].shape[0]
+    B = 70_000                       # more than one 65,536-row pipeline chunk
+    host, dev = PolicyBatch(model_path), PolicyBatch(model_path)
+    try:
+        d_obs = torch.zeros((B, 98), device="cuda"); d_vel = torch.zeros((B, 3), device="cuda")
+        d_act = torch.zeros((B, 12), device="cuda"); d_cmd = torch.zeros((B, CMD_DT.itemsize), device="cuda", dtype=torch.uint8)
+        h_act = np.zeros((B, 12), np.float32); h_cmd = np.zeros((B, CMD_DT.itemsize), np.uint8)
+        rng = np.random.default_rng(5)
+        for s in range(4):
+            idx = rng.integers(0, n_g, B)
+            raw = _raw_bytes(g, idx, rng.random(B) < 0.1)
+            host.step_host(raw, h_act, h_cmd, prec)
+            d_raw = torch.from_numpy(raw).cuda()
+            dev.step_device_cmd(d_raw.data_ptr(), d_vel.data_ptr(), d_obs.data_ptr(), d_act.data_ptr(), None, d_cmd.data_ptr(), B, prec)
+            torch.cuda.synchronize()
+            assert np.array_equal(bits(h_act), bits(d_act.cpu().numpy())), s
+            assert np.array_equal(h_cmd, d_cmd.cpu().numpy()), s
+        c = h_cmd.view(CMD_DT).reshape(B)
+        exp_q, _, _ = oracle.joint_targets(h_act, 0)
+        assert np.array_equal(c["q_des"].view(np.uint64), oracle.motor_command(exp_q, 0, 0)[0].view(np.uint64))
+        host.step_host_reset()       # zeroed histories again: first step equals a fresh handle's
+        fresh = PolicyBatch(model_path)
+        a1, a2 = np.zeros((256, 12), np.float32), np.zeros((256, 12), np.float32)
+        raw = _raw_bytes(g, list(range(256)))
+        host.step_host(raw, a1, None, prec); fresh.step_host(raw, a2, None, prec)
+        fresh.close()
+        assert np.array_equal(bits(a1), bits(a2))
+    finally:
+        host.close(); dev.close()
+
+
+def test_fleet_shards_rows_over_handles(torch_cuda, model_path, golden_loop):
+    """One process, several handles, one host thread each: the result equals a single handle's, row for row.  With one
+    GPU visible both shards run on device 0; with more the shards run on different devices."""
+    torch = torch_cuda
+    ndev = torch.cuda.device_count()
+    devices = (0, 1) if ndev >= 2 else (0, 0)
+    X = oracle.make_obs_d1(100_001, 98, seed=21)
+    one = PolicyBatch(model_path)
+    fl = Fleet(model_path, devices=devices)
+    try:
+        ref = one.infer_host(X, None, capi.PREC_FP16)
+        got = np.zeros_like(ref)
+        fl.infer_host(X, got, capi.PREC_FP16)
+        assert np.array_equal(bits(got), bits(ref))
+        g = golden_loop
+        raw = _raw_bytes(g, [i % 400 for i in range(5001)])
+        a1, a2 = np.zeros((5001, 12), np.float32), np.zeros((5001, 12), np.float32)
+        for _ in range(3):
+            one.step_host(raw, a1, None, capi.PREC_FP32)
+            fl.step_host(raw, a2, None, capi.PREC_FP32)
+            assert np.array_equal(bits(a1), bits(a2))
+    finally:
+        fl.close(); one.close()
+
+
+def test_one_thread_two_devices(torch_cuda, model_path, golden):
+    """The dynamic shared memory opt-in is a per-device function attribute: a second handle on another device, driven
+    from the same host thread, must launch the tcgen05 kernels as well (regression for a cache keyed by size only)."""
+    torch = torch_cuda
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs (run under gpurun --gpus 2)")
+    X = golden["d1_obs"]
+    outs = []
+    pbs = [PolicyBatch(model_path, device=d) for d in (0, 1)]
+    try:
+        for d, pb in enumerate(pbs):
+            with torch.cuda.device(d):
+                d_obs = torch.from_numpy(X).to(f"cuda:{d}"); d_act = torch.zeros((X.shape[0], 12), device=f"cuda:{d}")
+                for prec in (capi.PREC_FP16, capi.PREC_FP32):
+                    pb.infer_device(d_obs.data_ptr(), d_act.data_ptr(), X.shape[0], prec)
+                    torch.cuda.synchronize(d)
+                outs.append(d_act.cpu().numpy())
+        assert np.array_equal(bits(outs[0]), bits(outs[1]))
+    finally:
+        for pb in pbs:
+            pb.close()
