@@ -463,7 +463,15 @@ int launch_tc_t(go2p_handle* h, const TcArgs& a, cudaStream_t st) {
   }
   const long long tiles = (a.B + kTcTileM - 1) / kTcTileM;
   int grid = (int)std::min<long long>(tiles, h->sm_count - (h->resident ? 1 : 0));
-  kernel<<<grid, kTcThreads, smem, st>>>(a);
+  // programmatic stream serialization: the kernel's prologue may overlap the tail of the previous kernel of the stream
+  // (it waits for that kernel before touching observations / actions: griddepcontrol.wait in tc_mlp_kernel)
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(kTcThreads); lc.dynamicSmemBytes = smem; lc.stream = st;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = &attr; lc.numAttrs = 1;
+  CU_TRY(cudaLaunchKernelEx(&lc, kernel, a));
   h->last_launches++;
   CU_TRY(cudaGetLastError());
   return GO2P_OK;

@@ -241,6 +241,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
   block_sync();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // Programmatic dependent launch: everything above (barriers, TMEM, the weights' bulk copies -- the weights never
+  // change after go2p_create) may run while the previous kernel of the stream drains; observations are read and
+  // actions written only after that kernel has completed.  The next launch may start its own prologue as soon as
+  // this CTA's SM is free (a short batch per GPU, e.g. 1/8 of a sharded step, is otherwise launch-gap bound).
+  ptx::grid_dependency_wait();
+  ptx::grid_launch_dependents();
 
   const long long n_tiles = (a.B + kTcTileM - 1) / kTcTileM;
   const int n_local = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles b, b+G, ...

@@ -24,6 +24,12 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// wait: the grids this launch depends on (the previous kernel of the stream) have completed and their memory is visible
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// the dependent launch (the next kernel of the stream, if it opted in) may begin once every CTA has said so or exited
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
