@@ -79,6 +79,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// suspend-time hint of a blocking wait: a waiting warp sleeps in the barrier unit until the phase completes (it is woken
+// by the completing arrival) or this many nanoseconds pass, instead of re-polling every few hundred cycles -- the
+// re-polls of the warps that run ahead took issue slots from the warps they were waiting for
+#ifndef GO2P_MBAR_SUSPEND_NS
+#define GO2P_MBAR_SUSPEND_NS 4000
+#endif
+constexpr uint32_t kMbarSuspendNs = GO2P_MBAR_SUSPEND_NS;
+
 // the same operations on 32-bit shared-window addresses (no generic -> shared conversion per call)
 __device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -97,14 +105,14 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
       "{\n\t.reg .pred p;\n\t.reg .pred q;\n\t.reg .u32 n;\n\t"
       "mov.u32 n, 0;\n"
       "GO2P_WAITU:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra GO2P_DONEU;\n\t"
       "add.u32 n, n, 1;\n\t"
       "setp.lt.u32 q, n, 0x2000000;\n\t"
       "@q bra GO2P_WAITU;\n\t"
       "trap;\n"
       "GO2P_DONEU:\n\t}"
-      ::"r"(bar), "r"(parity) : "memory");
+      ::"r"(bar), "r"(parity), "r"(kMbarSuspendNs) : "memory");
 }
 
 // generic-proxy smem writes -> visible to the async proxy (tensor core / TMA reads)

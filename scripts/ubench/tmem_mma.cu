@@ -1,7 +1,7 @@
 // Micro-benchmark: tcgen05.ld / tcgen05.st latency seen by 16 epilogue warps while another warp keeps the tensor core busy
 // with tcgen05.mma (TS or SS form) on OTHER TMEM columns -- does the MMA's TMEM traffic slow the epilogue's, and vice versa?
 //   worker modes: 0 = ld x32 + wait::ld | 1 = 2 x ld x16 + wait::ld | 2 = st x16 + wait::st | 3 = ld x32 ; st x16 ; wait both
-//   mma modes:    0 = none | 1 = TS chains (A in TMEM) | 2 = SS chains (A in shared memory)
+//   mma modes:    0 = none | 1 = TS chains (A in TMEM) | 2 = SS chains (A in shared memory) | 3 = 1 SS step then 8 TS | 4 = 8 TS then 1 SS
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -40,7 +40,8 @@ __global__ void __launch_bounds__(17 * 32, 1) bench(long long* out, int wmode, i
       while (!stop) {
         if (ptx::elect_one_sync()) {
           for (int j = 0; j < 9; ++j) {
-            if (mmode == 1) ptx::mma_f16_ts(tb + 256u, tb + 448u + (uint32_t)(j & 7) * 8u, bdesc + (uint64_t)(j * 16), idesc, j > 0);
+            if (mmode == 1 || (mmode == 3 && j > 0) || (mmode == 4 && j < 8))
+              ptx::mma_f16_ts(tb + 256u, tb + 448u + (uint32_t)(j & 7) * 8u, bdesc + (uint64_t)(j * 16), idesc, j > 0);
             else ptx::mma_f16_ss(tb + 256u, adesc, bdesc + (uint64_t)(j * 16), idesc, j > 0);
           }
           ptx::mma_commit(&bar);
@@ -100,9 +101,9 @@ int main() {
   cudaMalloc(&out, 64); cudaMalloc(&sink, 4096);
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   const char* wn[] = {"ld x32 + wait", "2 x ld x16 + wait", "st x16 + wait", "st x16 ; ld x32 ; wait both"};
-  const char* mn[] = {"no MMA", "TS MMA chains", "SS MMA chains"};
-  for (int w = 0; w < 4; ++w)
-    for (int m = 0; m < 3; ++m) {
+  const char* mn[] = {"no MMA", "TS MMA chains", "SS MMA chains", "1 SS + 8 TS", "8 TS + 1 SS"};
+  for (int w = 0; w < 1; ++w)
+    for (int m = 0; m < 5; ++m) {
       cudaMemset(out, 0, 64);
       bench<<<1, 17 * 32, 64 * 1024>>>(out, w, m, sink);
       cudaError_t e = cudaDeviceSynchronize();
