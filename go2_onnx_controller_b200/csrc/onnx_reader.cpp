@@ -224,6 +224,26 @@ MlpModel parse_onnx_mlp(const uint8_t* data, size_t size) {
 
   std::string cur = m.input_name;
   bool bias_open = false;      // the last layer came from a MatMul / bias-less Gemm and may still take an Add
+  // Observation normaliser in front of the first Gemm (Sub / Add / Mul / Div with an initializer: x' = (x - mean) / std
+  // and friends): kept as x' = x * pre_scale + pre_shift per input column and folded into the first layer's weights
+  // and bias in double precision when that layer arrives.  The reference's bundled policy has none.
+  std::vector<double> pre_scale, pre_shift;
+  auto pre_apply = [&](const Node& n, const Tensor& c, char op) {
+    const size_t w = c.data.size();
+    if (w == 0) fail("node '" + n.name + "': empty normaliser constant");
+    if (pre_scale.empty()) { pre_scale.assign(w, 1.0); pre_shift.assign(w, 0.0); }
+    if (w != 1 && pre_scale.size() == 1) { pre_scale.assign(w, pre_scale[0]); pre_shift.assign(w, pre_shift[0]); }
+    if (w != 1 && w != pre_scale.size()) fail("node '" + n.name + "': normaliser constant width changes along the chain");
+    for (size_t k = 0; k < pre_scale.size(); ++k) {
+      const double v = (double)c.data[w == 1 ? 0 : k];
+      switch (op) {
+        case '+': pre_shift[k] += v; break;
+        case '-': pre_shift[k] -= v; break;
+        case '*': pre_scale[k] *= v; pre_shift[k] *= v; break;
+        default:  pre_scale[k] /= v; pre_shift[k] /= v; break;
+      }
+    }
+  };
   auto add_layer = [&](const Node& n, const Tensor& W, bool w_is_out_in, const Tensor* Bv) {
     if (W.dims.size() != 2) fail("node '" + n.name + "': weight must be 2-D");
     MlpLayer L;
@@ -237,6 +257,19 @@ MlpModel parse_onnx_mlp(const uint8_t* data, size_t size) {
       for (int k = 0; k < L.in; ++k)
         L.weight[size_t(o) * L.in + k] = w_is_out_in ? W.data[size_t(o) * L.in + k] : W.data[size_t(k) * L.out + o];
     if (Bv) L.bias = Bv->data; else L.bias.assign(size_t(L.out), 0.0f);
+    if (m.layers.empty() && !pre_scale.empty()) {
+      if (pre_scale.size() != 1 && (int)pre_scale.size() != L.in)
+        fail("node '" + n.name + "': observation normaliser width does not match the first layer's input");
+      for (int o = 0; o < L.out; ++o) {
+        double acc = (double)L.bias[o];
+        for (int k = 0; k < L.in; ++k) {
+          const size_t q = pre_scale.size() == 1 ? 0 : (size_t)k;
+          acc += (double)L.weight[size_t(o) * L.in + k] * pre_shift[q];
+          L.weight[size_t(o) * L.in + k] = (float)((double)L.weight[size_t(o) * L.in + k] * pre_scale[q]);
+        }
+        L.bias[o] = (float)acc;
+      }
+    }
     m.layers.push_back(std::move(L));
   };
   for (const Node& n : nodes) {
@@ -266,6 +299,16 @@ MlpModel parse_onnx_mlp(const uint8_t* data, size_t size) {
       add_layer(n, wi->second, false, nullptr);
       bias_open = true;
       cur = n.output;
+    } else if (m.layers.empty() && (n.op == "Sub" || n.op == "Add" || n.op == "Mul" || n.op == "Div")) {
+      // observation normaliser: (cur op constant); constant-first is accepted for the commutative ops only
+      if (n.inputs.size() != 2) fail("node '" + n.name + "': binary op with " + std::to_string(n.inputs.size()) + " inputs");
+      const bool first = n.inputs[0] == cur;
+      if (!first && (n.inputs[1] != cur || n.op == "Sub" || n.op == "Div"))
+        fail("node '" + n.name + "': " + n.op + " is not chained on '" + cur + "'");
+      auto ci = inits.find(first ? n.inputs[1] : n.inputs[0]);
+      if (ci == inits.end()) fail("node '" + n.name + "': normaliser operand must be an initializer");
+      pre_apply(n, ci->second, n.op == "Sub" ? '-' : n.op == "Add" ? '+' : n.op == "Mul" ? '*' : '/');
+      cur = n.output;
     } else if (n.op == "Add") {
       if (n.inputs.size() != 2 || !bias_open || m.layers.empty())
         fail("node '" + n.name + "': Add is only supported as the bias of the preceding MatMul / bias-less Gemm");
@@ -288,8 +331,17 @@ MlpModel parse_onnx_mlp(const uint8_t* data, size_t size) {
       m.layers.back().elu_alpha = it == n.fattr.end() ? 1.0f : it->second;
       bias_open = false;
       cur = n.output;
+    } else if (n.op == "Relu") {
+      // max(x, 0) == Elu with alpha = 0: every kernel's ELU epilogue serves it (the sign of an exact zero may differ)
+      if (m.layers.empty() || n.inputs.size() != 1 || n.inputs[0] != cur || m.layers.back().has_elu)
+        fail("node '" + n.name + "': Relu must directly follow a Gemm");
+      m.layers.back().has_elu = true;
+      m.layers.back().elu_alpha = 0.0f;
+      bias_open = false;
+      cur = n.output;
     } else {
-      fail("node '" + n.name + "': unsupported op_type '" + n.op + "' (supported: Gemm, MatMul, Add, Elu, Identity)");
+      fail("node '" + n.name + "': unsupported op_type '" + n.op +
+           "' (supported: Gemm, MatMul, Add, Elu, Relu, Identity; Sub/Add/Mul/Div with a constant in front of the first layer)");
     }
   }
   if (m.layers.empty()) fail("graph has no Gemm node");

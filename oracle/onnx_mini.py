@@ -271,6 +271,7 @@ def load_policy(path_or_bytes) -> Policy:
         raise ValueError("expected exactly one graph input and one graph output")
     cur = graph_inputs[0].name
     layers = []
+    pre_ops = []               # observation normaliser in front of the first layer: [(op, constant)] applied in order
     bias_open = False          # last layer came from MatMul / bias-less Gemm and may still take an Add
 
     def add_layer(n, w, b):
@@ -305,6 +306,17 @@ def load_policy(path_or_bytes) -> Policy:
             add_layer(n, np.ascontiguousarray(w.T) if w.ndim == 2 else w, None)
             bias_open = True
             cur = n.outputs[0]
+        elif not layers and n.op_type in ("Sub", "Add", "Mul", "Div"):
+            if len(n.inputs) != 2 or cur not in n.inputs:
+                raise ValueError(f"node '{n.name}': {n.op_type} is not chained on '{cur}'")
+            first = n.inputs[0] == cur
+            if not first and n.op_type in ("Sub", "Div"):
+                raise ValueError(f"node '{n.name}': constant {n.op_type} x is not supported")
+            other = n.inputs[1] if first else n.inputs[0]
+            if other not in inits:
+                raise ValueError(f"node '{n.name}': normaliser operand must be an initializer")
+            pre_ops.append((n.op_type, np.asarray(inits[other], np.float32).reshape(-1)))
+            cur = n.outputs[0]
         elif n.op_type == "Add":
             if len(n.inputs) != 2 or not bias_open or not layers or cur not in n.inputs:
                 raise ValueError(f"node '{n.name}': Add is only supported as the bias of the preceding MatMul")
@@ -324,6 +336,12 @@ def load_policy(path_or_bytes) -> Policy:
             layers[-1].elu_alpha = float(n.attrs.get("alpha", 1.0))
             bias_open = False
             cur = n.outputs[0]
+        elif n.op_type == "Relu":
+            if not layers or n.inputs[0] != cur or layers[-1].elu_alpha is not None:
+                raise ValueError(f"node '{n.name}': Relu must directly follow a Gemm")
+            layers[-1].elu_alpha = 0.0      # Elu(alpha = 0) == max(x, 0) up to the sign of zero
+            bias_open = False
+            cur = n.outputs[0]
         else:
             raise ValueError(f"node '{n.name}': unsupported op_type '{n.op_type}'")
     if not layers:
@@ -332,8 +350,10 @@ def load_policy(path_or_bytes) -> Policy:
         raise ValueError("graph output is not produced by the Gemm/Elu chain")
     if layers[-1].elu_alpha is not None:
         pass  # allowed: activation on the output layer
-    return Policy(layers, graph_inputs[0].name, outputs[0].name,
-                  graph_inputs[0].shape, outputs[0].shape, opset, producer)
+    pol = Policy(layers, graph_inputs[0].name, outputs[0].name,
+                 graph_inputs[0].shape, outputs[0].shape, opset, producer)
+    pol.pre_ops = pre_ops
+    return pol
 
 
 # ----------------------------------------------------------------------------
@@ -398,13 +418,21 @@ def _value_info(name: str, shape) -> bytes:
 def write_mlp_onnx(weights, biases, elu_alpha=1.0, *, batch=1, trans_b=True,
                    packed_dims=False, use_float_data=False,
                    input_name="observation", output_name="action",
-                   final_activation=False, form="gemm", identity_tail=False) -> bytes:
+                   final_activation=False, form="gemm", identity_tail=False, act_op="Elu", pre=()) -> bytes:
     """Serialise a Gemm/Elu MLP the way torch.onnx.export names things.
 
-    weights[i] is [out, in].  ``batch`` may be an int or a symbolic dim string.
+    weights[i] is [out, in].  ``batch`` may be an int or a symbolic dim string.  ``act_op`` "Relu" writes Relu nodes
+    instead of Elu; ``pre`` = [(op, constant)] writes an observation normaliser (Sub / Add / Mul / Div with an
+    initializer) in front of the first layer.
     """
     nodes, inits = b"", b""
     cur = input_name
+    for q, (op, const) in enumerate(pre):
+        cname, oname = f"norm.{q}", f"/norm/{op}_{q}_output_0"
+        nodes += _ld(1, _ld(1, cur.encode()) + _ld(1, cname.encode()) + _ld(2, oname.encode())
+                     + _ld(3, f"/norm/{op}_{q}".encode()) + _ld(4, op.encode()))
+        inits += _ld(5, _tensor(cname, np.asarray(const, np.float32), packed_dims, use_float_data))
+        cur = oname
     n = len(weights)
     for i, (w, b) in enumerate(zip(weights, biases)):
         idx = 2 * i
@@ -426,8 +454,9 @@ def write_mlp_onnx(weights, biases, elu_alpha=1.0, *, batch=1, trans_b=True,
             cur = gemm_out
             if not last or final_activation:
                 elu_out = tail_name if last else f"/{idx + 1}/Elu_output_0"
-                node = (_ld(1, cur.encode()) + _ld(2, elu_out.encode()) + _ld(3, f"/{idx + 1}/Elu".encode())
-                        + _ld(4, b"Elu") + _ld(5, _ld(1, b"alpha") + _f32(2, float(elu_alpha)) + _vi(20, 1)))
+                node = (_ld(1, cur.encode()) + _ld(2, elu_out.encode()) + _ld(3, f"/{idx + 1}/{act_op}".encode())
+                        + _ld(4, act_op.encode())
+                        + (_ld(5, _ld(1, b"alpha") + _f32(2, float(elu_alpha)) + _vi(20, 1)) if act_op == "Elu" else b""))
                 nodes += _ld(1, node)
                 cur = elu_out
             continue
@@ -443,8 +472,9 @@ def write_mlp_onnx(weights, biases, elu_alpha=1.0, *, batch=1, trans_b=True,
         cur = gemm_out
         if not last or final_activation:
             elu_out = tail_name if last else f"/{idx + 1}/Elu_output_0"
-            node = (_ld(1, cur.encode()) + _ld(2, elu_out.encode()) + _ld(3, f"/{idx + 1}/Elu".encode())
-                    + _ld(4, b"Elu") + _ld(5, _ld(1, b"alpha") + _f32(2, float(elu_alpha)) + _vi(20, 1)))
+            node = (_ld(1, cur.encode()) + _ld(2, elu_out.encode()) + _ld(3, f"/{idx + 1}/{act_op}".encode())
+                    + _ld(4, act_op.encode())
+                    + (_ld(5, _ld(1, b"alpha") + _f32(2, float(elu_alpha)) + _vi(20, 1)) if act_op == "Elu" else b""))
             nodes += _ld(1, node)
             cur = elu_out
     if identity_tail:

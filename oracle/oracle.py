@@ -70,11 +70,14 @@ def forward(policy: Policy, obs: np.ndarray, dtype=F64) -> np.ndarray:
     squeeze = x.ndim == 1
     if squeeze:
         x = x[None, :]
-    with np.errstate(over="ignore", invalid="ignore"):
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        for op, c in getattr(policy, "pre_ops", ()):        # observation normaliser nodes, as written in the graph
+            c = c.astype(dtype)
+            x = x - c if op == "Sub" else x + c if op == "Add" else x * c if op == "Mul" else x / c
         for layer in policy.layers:
             x = x @ layer.weight.astype(dtype).T + layer.bias.astype(dtype)
             if layer.elu_alpha is not None:
-                x = elu(x, layer.elu_alpha)
+                x = np.maximum(x, 0) if layer.elu_alpha == 0.0 else elu(x, layer.elu_alpha)
     return x[0] if squeeze else x
 
 

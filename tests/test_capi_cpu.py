@@ -108,6 +108,46 @@ def test_unsupported_op_is_rejected(lib, tmp_path):
     assert rc == capi.ERR_MODEL and "Erf" in msg
 
 
+def test_relu_and_observation_normaliser_are_folded_by_the_reader(lib, tmp_path):
+    """Relu is served as Elu(alpha = 0); Sub / Div (and Add / Mul) with a constant in front of the first
+    Gemm -- an observation normaliser -- are folded into that layer: W' = W * scale, b' = b + W @ shift."""
+    rng = np.random.default_rng(4)
+    dims = (20, 128, 128, 12)
+    ws = [rng.normal(0, 1.0 / np.sqrt(k), (n, k)).astype(np.float32) for k, n in zip(dims[:-1], dims[1:])]
+    bs = [rng.normal(0, 0.2, n).astype(np.float32) for n in dims[1:]]
+    mean, std = rng.normal(0, 1, 20).astype(np.float32), rng.uniform(0.5, 2, 20).astype(np.float32)
+    p = tmp_path / "norm_relu.onnx"
+    p.write_bytes(onnx_mini.write_mlp_onnx(ws, bs, 1.0, act_op="Relu", pre=[("Sub", mean), ("Div", std), ("Mul", np.float32([2.0]))]))
+    info, cs = capi.ModelInfo(), C.c_double()
+    assert lib.go2p_inspect_model(os.fspath(p).encode(), C.byref(info), C.byref(cs)) == capi.OK, lib.go2p_last_error()
+    assert [info.dims[i] for i in range(4)] == list(dims)
+    assert [info.has_elu[i] for i in range(3)] == [1, 1, 0] and info.elu_alpha[0] == 0.0 and info.elu_alpha[1] == 0.0
+    scale = 2.0 / std.astype(np.float64)
+    shift = -mean.astype(np.float64) / std.astype(np.float64) * 2.0
+    w0 = (ws[0].astype(np.float64) * scale).astype(np.float32)
+    b0 = (bs[0].astype(np.float64) + ws[0].astype(np.float64) @ shift).astype(np.float32)
+    exp = 0.0
+    for w, b in zip([w0] + ws[1:], [b0] + bs[1:]):
+        flat = np.concatenate([w.reshape(-1), b]).astype(np.float64)
+        exp += float(((np.arange(flat.size) % 97) + 1) @ flat)
+    assert abs(cs.value - exp) <= 1e-9 * max(1.0, abs(exp))
+    # the oracle evaluates the graph as written (normaliser nodes applied to the input, max(x, 0))
+    from oracle import oracle
+    pol = oracle.load_policy(str(p))
+    x = rng.normal(0, 1, (7, 20)).astype(np.float32)
+    h = (x.astype(np.float64) - mean) / std * 2.0
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        h = h @ w.T.astype(np.float64) + b
+        if i < 2:
+            h = np.maximum(h, 0)
+    assert np.abs(oracle.forward(pol, x) - h).max() <= 1e-12
+    # a normaliser after the first layer, or constant / x, is not a normaliser: rejected with a message
+    bad = onnx_mini.write_mlp_onnx(ws, bs, 1.0).replace(b"Elu", b"Div", 1)
+    q = tmp_path / "bad.onnx"
+    q.write_bytes(bad)
+    assert lib.go2p_inspect_model(os.fspath(q).encode(), C.byref(info), None) == capi.ERR_MODEL
+
+
 @pytest.mark.skipif(not _no_gpu(), reason="uses the no-device error to tell 'parsed' from 'rejected'")
 @pytest.mark.parametrize("form,tail", [("matmul_add", False), ("mixed", True), ("gemm", True)])
 def test_other_spellings_of_linear_layers_parse(lib, tmp_path, form, tail):

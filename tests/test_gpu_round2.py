@@ -235,3 +235,40 @@ def test_one_thread_two_devices(torch_cuda, model_path, golden):
     finally:
         for pb in pbs:
             pb.close()
+
+
+def test_relu_policy_with_observation_normaliser_all_paths(torch_cuda, tmp_path):
+    """a Relu policy with a Sub/Div observation normaliser in the graph (folded by the reader) agrees with
+    the oracle, which evaluates the graph as written, on the fp32 path (1e-5), the tcgen05 path and batch-1 act()."""
+    from go2_onnx_controller_b200 import ONNXActor
+    from oracle import onnx_mini
+    torch = torch_cuda
+    rng = np.random.default_rng(8)
+    dims = (60, 128, 128, 128, 12)
+    ws = [rng.normal(0, 1.0 / np.sqrt(k), (n, k)).astype(np.float32) for k, n in zip(dims[:-1], dims[1:])]
+    bs = [rng.normal(0, 0.2, n).astype(np.float32) for n in dims[1:]]
+    mean, std = rng.normal(0, 2, 60).astype(np.float32), rng.uniform(0.5, 3, 60).astype(np.float32)
+    path = tmp_path / "norm_relu.onnx"
+    path.write_bytes(onnx_mini.write_mlp_onnx(ws, bs, 1.0, act_op="Relu", pre=[("Sub", mean), ("Div", std)]))
+    pol = oracle.load_policy(str(path))
+    X = (rng.normal(0, 1, (1500, 60)) * std + mean).astype(np.float32)
+    ref = oracle.forward(pol, X)
+    pb = PolicyBatch(str(path))
+    try:
+        d_obs = torch.from_numpy(X).cuda(); d_act = torch.zeros((1500, 12), device="cuda")
+        for prec, tol in ((capi.PREC_FP32, 1e-5), (capi.PREC_FP16, 1e-2), (capi.PREC_BF16, 7e-2)):
+            pb.infer_device(d_obs.data_ptr(), d_act.data_ptr(), 1500, prec)
+            torch.cuda.synchronize()
+            err = (np.abs(d_act.cpu().numpy() - ref) / np.maximum(1, np.abs(ref))).max()
+            assert err <= tol, (prec, err)
+    finally:
+        pb.close()
+    obs, act = np.zeros(60, np.float32), np.zeros(12, np.float32)
+    a = ONNXActor(str(path), obs, act)
+    try:
+        for i in range(5):
+            obs[:] = X[i]
+            a.act()
+            assert (np.abs(act - ref[i]) / np.maximum(1, np.abs(ref[i]))).max() <= 1e-5
+    finally:
+        a.close()
