@@ -72,7 +72,7 @@ struct go2p_handle {
   bool wide_ok = false;
   uint16_t* d_wpack[2] = {nullptr, nullptr};   // [0] bf16, [1] fp16
   int k0p = 0;
-  size_t tc_attr_smem[2] = {0, 0};             // dynamic shared memory opted in for tc_mlp_kernel<bf16|fp16> on this device
+  size_t tc_attr_smem[4] = {0, 0, 0, 0};       // dynamic shared memory opted in for tc_mlp_kernel<bf16|fp16, plain|fused> on this device
   bool b1_attr_set = false;                    // same for the one-shot batch-1 kernel
   size_t so_attr_smem = 0;                     // same for small_out_kernel
   WideModel wide{};
@@ -452,14 +452,15 @@ int launch_fp32(go2p_handle* h, const float* d_obs, const int32_t* d_button0, fl
   return GO2P_OK;
 }
 
-template <bool kFp16>
+template <bool kFp16, bool kFused>
 int launch_tc_t(go2p_handle* h, const TcArgs& a, cudaStream_t st) {
   const size_t smem = tc_smem_bytes(a);
-  auto kernel = tc_mlp_kernel<kFp16>;
+  auto kernel = tc_mlp_kernel<kFp16, kFused>;
   // the opt-in is a per-device function attribute: remembered per handle (one handle = one device)
-  if (h->tc_attr_smem[kFp16 ? 1 : 0] != smem) {
+  size_t& configured = h->tc_attr_smem[(kFp16 ? 1 : 0) + (kFused ? 2 : 0)];
+  if (configured != smem) {
     CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    h->tc_attr_smem[kFp16 ? 1 : 0] = smem;
+    configured = smem;
   }
   const long long tiles = (a.B + kTcTileM - 1) / kTcTileM;
   int grid = (int)std::min<long long>(tiles, h->sm_count - (h->resident ? 1 : 0));
@@ -477,8 +478,10 @@ int launch_tc_t(go2p_handle* h, const TcArgs& a, cudaStream_t st) {
   return GO2P_OK;
 }
 
+// raw != null: the fused controller step (A1-A6 in the conversion job): d_obs is the robots' history, updated in place
 int launch_tc(go2p_handle* h, const float* d_obs, const int32_t* d_button0, float* d_act, double* d_qdes,
-              MotorCmdDev* d_cmd, int64_t B, bool fp16, uint32_t flags, cudaStream_t st) {
+              MotorCmdDev* d_cmd, int64_t B, bool fp16, uint32_t flags, cudaStream_t st,
+              const RawStateDev* raw = nullptr, float* d_vel_cmd = nullptr) {
   if ((reinterpret_cast<uintptr_t>(d_obs) & 15) || (reinterpret_cast<uintptr_t>(d_act) & 15) ||
       (d_qdes && (reinterpret_cast<uintptr_t>(d_qdes) & 15)))
     return fail(GO2P_ERR_INVALID, "tensor-core path needs 16-byte aligned obs/act/qdes device pointers");
@@ -500,7 +503,9 @@ int launch_tc(go2p_handle* h, const float* d_obs, const int32_t* d_button0, floa
 #ifdef GO2P_TC_TRACE
   if (const char* e = std::getenv("GO2P_TC_TRACE_PTR")) a.trace = reinterpret_cast<unsigned long long*>(std::strtoull(e, nullptr, 0));
 #endif
-  return fp16 ? launch_tc_t<true>(h, a, st) : launch_tc_t<false>(h, a, st);
+  a.raw = raw; a.obs_rw = const_cast<float*>(d_obs); a.vel_cmd = d_vel_cmd; a.H = h->cc.H; a.foot_threshold = h->cc.foot_threshold;
+  if (raw) return fp16 ? launch_tc_t<true, true>(h, a, st) : launch_tc_t<false, true>(h, a, st);
+  return fp16 ? launch_tc_t<true, false>(h, a, st) : launch_tc_t<false, false>(h, a, st);
 }
 
 }  // namespace
@@ -1027,6 +1032,15 @@ namespace {
 // publish() for B robots on device buffers; button_scratch [B] receives the dead-man buttons for the epilogue
 int step_batch_on(go2p_handle* h, const go2p_raw_state* d_raw, float* d_vel_cmd, float* d_obs, float* d_action, double* d_qdes,
                   go2p_motor_cmd* d_cmd, int32_t* button_scratch, int64_t B, int precision, cudaStream_t st) {
+  const uint32_t all_flags = GO2P_F_CLAMP_MASK | (d_qdes ? GO2P_F_QDES : 0u) | (d_cmd ? GO2P_F_MOTOR_CMD : 0u);
+  if (h->tc_ok && (precision == GO2P_PREC_FP16 || precision == GO2P_PREC_BF16) && (h->dm.in_dim & 1) == 0 &&
+      !(reinterpret_cast<uintptr_t>(d_obs) & 15) && !(reinterpret_cast<uintptr_t>(d_action) & 15) &&
+      !(d_qdes && (reinterpret_cast<uintptr_t>(d_qdes) & 15)) && !(d_cmd && (reinterpret_cast<uintptr_t>(d_cmd) & 15))) {
+    // ONE launch: A1-A6 run inside the policy kernel's conversion job, the newest frame never round-trips HBM
+    h->last_launches = 0;
+    return launch_tc(h, d_obs, nullptr, d_action, d_qdes, reinterpret_cast<MotorCmdDev*>(d_cmd), B, precision == GO2P_PREC_FP16,
+                     all_flags, st, reinterpret_cast<const RawStateDev*>(d_raw), d_vel_cmd);
+  }
   // A1-A6: d_action still holds the previous published action here
   launch_assemble_batch(reinterpret_cast<const RawStateDev*>(d_raw), d_action, d_vel_cmd, d_obs, B, h->cc, button_scratch,
                         h->sm_count, st);

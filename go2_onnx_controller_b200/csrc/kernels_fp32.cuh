@@ -176,11 +176,7 @@ __global__ void post_kernel(float* __restrict__ act, long long total, int out_di
 
 // A1-A6 for B robots: one thread per observation element, history kept in the obs rows themselves
 // (term-major, oldest frame first; reference: controller.cpp:200-212).  raw words as in kernels_b1.cuh.
-struct RawStateDev {
-  float quat[4]; float gyro[3]; float q[12]; float dq[12]; float axes[4];
-  int16_t foot_force[4]; int32_t joy_valid; int32_t button0;
-};
-static_assert(sizeof(RawStateDev) == 4 * 35 + 8 + 8, "must match go2p_raw_state");
+// (RawStateDev: policy_dev.cuh)
 
 // button0_out (optional): the dead-man button of every robot as int32 [B], the form the batched epilogue reads.
 // A warp takes 32 robots at a time:

@@ -29,6 +29,7 @@
 //   * one elected thread issues every tcgen05.mma and signals completion with tcgen05.commit; ONE pool of 16 worker
 //     warps walks the jobs of both slots alternately, so a slot's MMAs run while the pool works on the other slot.
 #pragma once
+#include "kernels_b1.cuh"      // gravity_all, vel_cmd_component: the same device functions as the batch-1 kernel
 #include "policy_dev.cuh"
 #include "ptx_sm100.cuh"
 
@@ -61,6 +62,13 @@ struct TcArgs {
   double q0[kDof];
   MotorCmdDev* cmd;          // [B] send_command arguments in Unitree motor order (flag 4) or null
   float kp, kd, kp_deadman;
+  // fused controller step (go2p_step_batch, tc_mlp_kernel<., true>): A1-A6 run in the conversion job.  obs_rw holds
+  // every robot's history (== its previous observation) and is updated in place; act holds the previous published
+  // action on entry (read by the assembly) and the new one on return; button0 comes from the raw state.
+  const RawStateDev* raw;    // [B]
+  float* obs_rw;             // [B, 49*H]  (== obs)
+  float* vel_cmd;            // [B, 3] last joystick command (in/out)
+  int H, foot_threshold;
   unsigned long long* trace;   // debug timeline (GO2P_TC_TRACE): [0] = count, then (event, clock64) pairs; CTA 0 only
 };
 
@@ -90,7 +98,77 @@ __host__ __device__ inline size_t tc_weight_bytes(const TcArgs& a) {
   return s;
 }
 __host__ __device__ inline size_t tc_stage_bytes(const TcArgs& a) { return ((size_t)kTcTileM * a.in_dim * 4 + 127) & ~(size_t)127; }
-__host__ __device__ inline size_t tc_smem_bytes(const TcArgs& a) { return tc_weight_bytes(a) + 2 * tc_stage_bytes(a) + 256; }
+__host__ __device__ inline size_t tc_smem_bytes(const TcArgs& a) { return tc_weight_bytes(a) + 2 * tc_stage_bytes(a) + 256 + 4 * kTcTileM * 4; }
+
+// ---- fused A1-A6: history shift + newest frame of one observation term, in place in the row's shared-memory copy
+// (term-major layout, oldest frame first inside a term: controller.hpp:45-68, controller.cpp:200-212)
+template <int kW>
+__device__ __forceinline__ void tc_shift_append(float* term, int H, const float (&cur)[kW]) {
+#pragma unroll 1
+  for (int f = 0; f + 1 < H; ++f) {
+#pragma unroll
+    for (int j = 0; j < kW; ++j) term[f * kW + j] = term[(f + 1) * kW + j];
+  }
+#pragma unroll
+  for (int j = 0; j < kW; ++j) term[(H - 1) * kW + j] = cur[j];
+}
+
+// Column block cb of a lane quarter updates "its" terms of row `srow` (robot `grow`): cb 0 gravity / angular velocity /
+// joystick command, cb 1 joint positions, cb 2 joint velocities, cb 3 previous action / foot contacts (+ the dead-man
+// button for the output job).  Bit-exact rules as in kernels_b1.cuh (same device functions).
+__device__ __forceinline__ void tc_update_terms(const TcArgs& a, int cb, float* srow, long long grow, int* button_out) {
+  const uint32_t* rw = reinterpret_cast<const uint32_t*>(a.raw + grow);
+  const float* rf = reinterpret_cast<const float*>(rw);
+  const int H = a.H;
+  if (cb == 0) {
+    const float quat[4] = {rf[0], rf[1], rf[2], rf[3]};
+    float g[3];
+    gravity_all(quat, g);
+    const float w[3] = {rf[4], rf[5], rf[6]};
+    float cmd[3];
+    if (rw[37]) {                                        // joy_ && !axes.empty() (controller.cpp:173)
+      const float axes[4] = {rf[31], rf[32], rf[33], rf[34]};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { cmd[c] = vel_cmd_component(axes, c); a.vel_cmd[grow * 3 + c] = cmd[c]; }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) cmd[c] = a.vel_cmd[grow * 3 + c];
+    }
+    tc_shift_append<3>(srow, H, g);
+    tc_shift_append<3>(srow + 3 * H, H, w);
+    tc_shift_append<3>(srow + 6 * H, H, cmd);
+  } else if (cb == 1) {
+    float q[kDof];
+#pragma unroll
+    for (int c = 0; c < kDof; ++c) q[c] = __double2float_rn(__dsub_rn((double)rf[7 + c], a.q0[c]));   // controller.cpp:194-197
+    tc_shift_append<kDof>(srow + 9 * H, H, q);
+  } else if (cb == 2) {
+    float dq[kDof];
+#pragma unroll
+    for (int c = 0; c < kDof; ++c) dq[c] = rf[19 + c];
+    tc_shift_append<kDof>(srow + 21 * H, H, dq);
+  } else {
+    float pa[kDof];
+    const float4* p4 = reinterpret_cast<const float4*>(a.act + grow * kDof);      // previous published action
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { const float4 t = p4[q]; pa[4 * q] = t.x; pa[4 * q + 1] = t.y; pa[4 * q + 2] = t.z; pa[4 * q + 3] = t.w; }
+    float ct[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int p = c ^ 1;                                                          // [1,0,3,2] (controller.hpp:99-103)
+      const int force = (int)(int16_t)(uint16_t)(rw[35 + (p >> 1)] >> (16 * (p & 1)));
+      ct[c] = (force >= a.foot_threshold) ? 1.0f : 0.0f;
+    }
+    tc_shift_append<kDof>(srow + 33 * H, H, pa);
+    tc_shift_append<4>(srow + 45 * H, H, ct);
+    *button_out = (int)rw[38];
+  }
+}
+// the term ranges (floats) column block cb owns in a row: [lo, hi)
+__device__ __forceinline__ void tc_term_range(int cb, int H, int& lo, int& hi) {
+  lo = cb == 0 ? 0 : cb == 1 ? 9 * H : cb == 2 ? 21 * H : 33 * H;
+  hi = cb == 0 ? 9 * H : cb == 1 ? 21 * H : cb == 2 ? 33 * H : 49 * H;
+}
 
 // c*(2^z - 1) for z < 0 on a packed fp16 pair without the MUFU: clamp at -13 (2^-13 is below the resolution of the
 // result), split z = -k + r with the 1536 = 1.5*2^10 rounding trick (k = 0..13 lands in the low mantissa bits of u),
@@ -198,7 +276,7 @@ __device__ __noinline__ void tc_out_generic(const TcArgs& a, uint32_t o_t, long 
   if ((a.flags & 4u) && a.cmd) store_gains(a.cmd, row, b0, a.kp, a.kd, a.kp_deadman);
 }
 
-template <bool kFp16>
+template <bool kFp16, bool kFused>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -213,6 +291,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
   uint64_t* a_blk = bars + 6;       // [2][4], entry [s][0] used: A operand of slot s's next layer ready (16 arrivals)
   uint64_t* w_full = bars + 14;     // [kMaxLayers]  layer weights landed in shared memory (completes once)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14 + kMaxLayers);
+  int* s_button = reinterpret_cast<int*>(stage0 + 2 * stage_bytes + 256);   // [2 slots][2 tile parities][128] fused step: the rows' dead-man buttons
+  // (the conversion of a slot's next tile may run, in the column block that has no output work, while the other column
+  // blocks still read the current tile's buttons: consecutive tiles of a slot use different halves)
 
   // ---- one-time setup: barriers, TMEM; the weights arrive as one bulk async copy per layer, each with its own
   // mbarrier, so the first tile's conversion and layer-0 MMA do not wait for the deeper layers' weights (matters for
@@ -355,7 +436,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
       ptx::mbar_wait(&obs_full[s], (uint32_t)(pair & 1));
       TC_TRACE(0x400u | (uint32_t)s);
       const int c8_hi = min(n8, 2 * cb + 2);
-      if (valid == kTcTileM && even) {
+      if constexpr (kFused) {
+        // ---- A1-A6 (controller.cpp:173-212): the stage holds the tile's previous observations (== histories);
+        // shift them by one frame and append the newest frame from the raw states, in place, then send the rows
+        // back to the caller's history buffer with one bulk copy per lane quarter while the layers run
+        float* srow = reinterpret_cast<float*>(stage0 + s * stage_bytes) + (size_t)m * a.in_dim;
+        const bool full = valid == kTcTileM;
+        if (m < valid) {
+          int lo, hi;
+          tc_term_range(cb, a.H, lo, hi);
+          if (!full) for (int k = lo; k < hi; ++k) srow[k] = a.obs_rw[(row0 + m) * a.in_dim + k];   // ragged tile: no bulk load
+          tc_update_terms(a, cb, srow, row0 + m, &s_button[(s * 2 + (pair & 1)) * kTcTileM + m]);
+          if (!full) for (int k = lo; k < hi; ++k) a.obs_rw[(row0 + m) * a.in_dim + k] = srow[k];
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");       // the quarter's four column blocks
+        if (full && cb == 0 && lane == 0)
+          ptx::bulk_s2g(a.obs_rw + (row0 + quarter * 32) * a.in_dim, srow, (uint32_t)(32 * a.in_dim * 4));
+      }
+      if ((valid == kTcTileM || kFused) && even) {
         // full tile in shared memory, rows 8-byte aligned: vector loads, uniform per-pair classification
         const float2* r2 = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(stage0 + s * stage_bytes) + (size_t)m * a.in_dim);
 #pragma unroll 1
@@ -376,11 +476,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
           ptx::tmem_st_x8(a0_t + (uint32_t)(32 * (c8 >> 1) + 8 * (c8 & 1)), q);
         }
       } else {
-        const float* rowp = (valid == kTcTileM) ? reinterpret_cast<const float*>(stage0 + s * stage_bytes) + (size_t)m * a.in_dim
-                                                : a.obs + (row0 + m) * a.in_dim;
+        const float* rowp = (valid == kTcTileM || kFused) ? reinterpret_cast<const float*>(stage0 + s * stage_bytes) + (size_t)m * a.in_dim
+                                                          : a.obs + (row0 + m) * a.in_dim;
         tc_conv_slow<kFp16>(a, rowp, m < valid, 2 * cb, c8_hi, a0_t);
       }
       ptx::tc_wait_st();
+      if constexpr (kFused) { if (cb == 0 && lane == 0) ptx::bulk_wait_read(); }   // the stage may be refilled after this job
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&a_blk[s * kTcBlocks]);
@@ -409,7 +510,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
 #pragma unroll
             for (int j = 0; j < 4; ++j) o[j] = __uint_as_float(v[j]);
             if (a.flags & 1u) {
-              const int b0 = s ? b0_s1 : b0_s0;          // loaded two jobs ahead (see the E loop)
+              // loaded two jobs ahead (see the E loop); fused step: taken from the raw state by the conversion job
+              const int b0 = kFused ? s_button[(s * 2 + (pair & 1)) * kTcTileM + m] : (s ? b0_s1 : b0_s0);
 #pragma unroll
               for (int j = 0; j < 4; ++j) o[j] = clamp_mask(o[j], a.action_limit, b0);
             }
@@ -428,7 +530,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
                 MotorCmdDev* c = a.cmd + row;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) c->q_des[(j ^ 1) * 3 + cb] = qd[j];
-                if (cb == 0) store_gains(a.cmd, row, s ? b0_s1 : b0_s0, a.kp, a.kd, a.kp_deadman);
+                if (cb == 0) store_gains(a.cmd, row, kFused ? s_button[(s * 2 + (pair & 1)) * kTcTileM + m] : (s ? b0_s1 : b0_s0), a.kp, a.kd, a.kp_deadman);
               }
             }
           }
@@ -515,6 +617,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
   }
 
   // ---- teardown
+  if constexpr (kFused) ptx::bulk_wait_all();      // this thread's bulk stores of updated observation rows are complete
   ptx::tc_fence_before();
   block_sync();
   if (warp == kTcCtrlWarp0) {

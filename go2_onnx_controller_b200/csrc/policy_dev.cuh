@@ -36,6 +36,15 @@ struct CtrlConst {
   float kp, kd;          // controller.hpp:119-120 (ROS parameters; go2p_set_gains)
 };
 
+// Everything publish() reads from the outside world for one robot and one control step (include/go2policy.h:
+// go2p_raw_state); as 32-bit words: quat 0-3, gyro 4-6, q 7-18, dq 19-30, axes 31-34, foot_force 35-36 (4 x int16),
+// joy_valid 37, button0 38.
+struct RawStateDev {
+  float quat[4]; float gyro[3]; float q[12]; float dq[12]; float axes[4];
+  int16_t foot_force[4]; int32_t joy_valid; int32_t button0;
+};
+static_assert(sizeof(RawStateDev) == 4 * 35 + 8 + 8, "must match go2p_raw_state");
+
 // What Go2RobotInterface::send_command receives from publish() (controller.cpp:235-251), in UNITREE motor order:
 // motor u = leg_u*3 + joint with legs FR, FL, RR, RL and joints hip, thigh, calf, while the policy works in Isaac order
 // i = joint*4 + leg_i with legs FL, FR, RL, RR (controller.hpp:168-170) -- the same left/right swap as the foot

@@ -384,12 +384,12 @@ def test_batched_observation_assembly_bit_exact(torch_cuda, pb, golden_loop):
 
 @pytest.mark.parametrize("prec", [capi.PREC_FP32, capi.PREC_FP16])
 def test_batched_controller_step_closed_loop(torch_cuda, pb, policy, golden_loop, prec):
-    """go2p_step_batch = publish() for B robots in two launches (A1-A6, then A7+A9+A11), per-robot history on the
-    device, the published action fed back as the next step's previous action (reference: controller.cpp:173-251).
+    """go2p_step_batch = publish() for B robots (one fused launch on the tensor-core path; assembly + policy launches
+    on the fp32 path), per-robot history on the device, the published action fed back as the next step's previous action (reference: controller.cpp:173-251).
     Every step is compared with the restated publish() re-synchronised to the device's own published action."""
     torch = torch_cuda
     g = golden_loop
-    B, steps = 80, 6
+    B, steps = 333, 6           # two full 128-row tiles + a ragged one
     n_g = g["obs"].shape[0]
     states = [oracle.ControllerState(H=2) for _ in range(B)]
     d_obs = torch.zeros((B, 98), device="cuda", dtype=torch.float32)
@@ -408,7 +408,9 @@ def test_batched_controller_step_closed_loop(torch_cuda, pb, policy, golden_loop
         d_raw = torch.from_numpy(np.frombuffer(bytes(raws), np.uint8).copy()).cuda()
         pb.step_device(d_raw.data_ptr(), d_vel.data_ptr(), d_obs.data_ptr(), d_act.data_ptr(), d_q.data_ptr(), B, prec)
         torch.cuda.synchronize()
-        assert pb.last_launches() == (5 if prec == capi.PREC_FP32 else 2)
+        # fp32: assembly + 3 Gemm launches + output kernel; tensor-core precisions: ONE launch (A1-A6 fused into the
+        # policy kernel's conversion job)
+        assert pb.last_launches() == (5 if prec == capi.PREC_FP32 else 1)
         obs, act, qd = d_obs.cpu().numpy(), d_act.cpu().numpy(), d_q.cpu().numpy()
         for b in range(B):
             raw = raw_py(g, idx[b])
