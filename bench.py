@@ -495,9 +495,12 @@ def main():
         torch.cuda.synchronize()
         n_ctl = max(3, min(args.steps, 10))
         ctl_ms = timed_loop(ctl_step, n_ctl) / n_ctl
+        step_bytes = 156 + 392 + 48 + 12 + 392 + 48 + 96 + 12     # raw, history in, prev action, cmd in | history out, action, q_des, cmd out
         line["batched_step"] = {"robots": rows, "ms_per_step": ctl_ms, "robot_steps_per_sec": rows / (ctl_ms * 1e-3),
-                                "launches_per_step": pb.last_launches(),
-                                "note": "go2p_step_batch on device buffers: A1-A6 + A7 + A9 + A11, per-robot state in HBM"}
+                                "launches_per_step": pb.last_launches(), "algorithmic_bytes_per_robot_step": step_bytes,
+                                "hbm_frac": step_bytes * rows / (ctl_ms * 1e-3) / 1e9 / hbm_peak,
+                                "note": "go2p_step_batch on device buffers: A1-A6 + A7 + A9 + A11 in one launch (assembly fused "
+                                        "into the policy kernel's conversion job), per-robot state in HBM"}
         del d_raw, s_obs, s_vel, s_act, s_q
     if rank == 0 and world == 1 and not args.no_b1 and not args.no_extras:
         # BASELINE.json configs[1]: batch-1 closed loop, fused pre/post, resident kernel

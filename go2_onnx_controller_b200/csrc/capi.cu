@@ -1033,7 +1033,11 @@ namespace {
 int step_batch_on(go2p_handle* h, const go2p_raw_state* d_raw, float* d_vel_cmd, float* d_obs, float* d_action, double* d_qdes,
                   go2p_motor_cmd* d_cmd, int32_t* button_scratch, int64_t B, int precision, cudaStream_t st) {
   const uint32_t all_flags = GO2P_F_CLAMP_MASK | (d_qdes ? GO2P_F_QDES : 0u) | (d_cmd ? GO2P_F_MOTOR_CMD : 0u);
+  TcArgs probe{};
+  probe.n_layers = h->dm.n_layers; probe.in_dim = h->dm.in_dim; probe.k0p = h->k0p;
+  probe.raw = reinterpret_cast<const RawStateDev*>(d_raw);          // the fused kernel also stages the raw states
   if (h->tc_ok && (precision == GO2P_PREC_FP16 || precision == GO2P_PREC_BF16) && (h->dm.in_dim & 1) == 0 &&
+      tc_smem_bytes(probe) <= (size_t)227 * 1024 && !(reinterpret_cast<uintptr_t>(d_raw) & 15) &&
       !(reinterpret_cast<uintptr_t>(d_obs) & 15) && !(reinterpret_cast<uintptr_t>(d_action) & 15) &&
       !(d_qdes && (reinterpret_cast<uintptr_t>(d_qdes) & 15)) && !(d_cmd && (reinterpret_cast<uintptr_t>(d_cmd) & 15))) {
     // ONE launch: A1-A6 run inside the policy kernel's conversion job, the newest frame never round-trips HBM

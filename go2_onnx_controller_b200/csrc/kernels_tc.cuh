@@ -98,7 +98,11 @@ __host__ __device__ inline size_t tc_weight_bytes(const TcArgs& a) {
   return s;
 }
 __host__ __device__ inline size_t tc_stage_bytes(const TcArgs& a) { return ((size_t)kTcTileM * a.in_dim * 4 + 127) & ~(size_t)127; }
-__host__ __device__ inline size_t tc_smem_bytes(const TcArgs& a) { return tc_weight_bytes(a) + 2 * tc_stage_bytes(a) + 256 + 4 * kTcTileM * 4; }
+constexpr int kTcRawWords = 39;                               // sizeof(RawStateDev) / 4
+constexpr int kTcRawStageBytes = kTcTileM * kTcRawWords * 4;    // fused step: one tile's raw states (128 x 156 B, contiguous)
+__host__ __device__ inline size_t tc_smem_bytes(const TcArgs& a) {
+  return tc_weight_bytes(a) + 2 * tc_stage_bytes(a) + 256 + 4 * kTcTileM * 4 + (a.raw ? kTcRawStageBytes : 0);
+}
 
 // ---- fused A1-A6: history shift + newest frame of one observation term, in place in the row's shared-memory copy
 // (term-major layout, oldest frame first inside a term: controller.hpp:45-68, controller.cpp:200-212)
@@ -116,9 +120,8 @@ __device__ __forceinline__ void tc_shift_append(float* term, int H, const float 
 // Column block cb of a lane quarter updates "its" terms of row `srow` (robot `grow`): cb 0 gravity / angular velocity /
 // joystick command, cb 1 joint positions, cb 2 joint velocities, cb 3 previous action / foot contacts (+ the dead-man
 // button for the output job).  Bit-exact rules as in kernels_b1.cuh (same device functions).
-__device__ __forceinline__ void tc_update_terms(const TcArgs& a, int cb, float* srow, long long grow, int* button_out) {
-  const uint32_t* rw = reinterpret_cast<const uint32_t*>(a.raw + grow);
-  const float* rf = reinterpret_cast<const float*>(rw);
+__device__ __forceinline__ void tc_update_terms(const TcArgs& a, int cb, float* srow, const uint32_t* rw, long long grow, int* button_out) {
+  const float* rf = reinterpret_cast<const float*>(rw);     // this robot's raw state: 39 words (shared-memory stage, or global for a ragged tile)
   const int H = a.H;
   if (cb == 0) {
     const float quat[4] = {rf[0], rf[1], rf[2], rf[3]};
@@ -291,6 +294,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
   uint64_t* a_blk = bars + 6;       // [2][4], entry [s][0] used: A operand of slot s's next layer ready (16 arrivals)
   uint64_t* w_full = bars + 14;     // [kMaxLayers]  layer weights landed in shared memory (completes once)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14 + kMaxLayers);
+  // fused step: ONE stage for the raw states of the tile whose conversion comes next (the two slots convert alternately)
+  uint32_t* s_raw = reinterpret_cast<uint32_t*>(stage0 + 2 * stage_bytes + 256 + 4 * kTcTileM * 4);
+  uint64_t* raw_full = bars + 2;    // raw states of CTA-local tile i landed (phase i & 1)
   int* s_button = reinterpret_cast<int*>(stage0 + 2 * stage_bytes + 256);   // [2 slots][2 tile parities][128] fused step: the rows' dead-man buttons
   // (the conversion of a slot's next tile may run, in the column block that has no output work, while the other column
   // blocks still read the current tile's buttons: consecutive tiles of a slot use different halves)
@@ -302,6 +308,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
     if (lane == 0) {
       for (int s = 0; s < 2; ++s) {
         ptx::mbar_init(&obs_full[s], 1);
+        if (s == 0) ptx::mbar_init(raw_full, 1);
         ptx::mbar_init(&acc_full[s], 1);
         ptx::mbar_init(&a_blk[s * kTcBlocks], kTcWorkers);   // one A-ready barrier per slot: every worker warp arrives once per job
       }
@@ -357,7 +364,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
         ptx::mbar_arrive(&obs_full[s]);      // ragged last tile: the pool reads global memory directly
       }
     };
-    if (s < n_local && ptx::elect_one_sync()) load_tile(s);
+    // fused step: tile i's raw states (contiguous 19,968 B) -> the raw stage; issued when conversion i-1 (the other
+    // slot's) has signalled, i.e. when every warp is done with the stage
+    auto load_raw = [&](int i) {
+      const long long row0 = (blockIdx.x + (long long)i * gridDim.x) * kTcTileM;
+      if (a.B - row0 >= kTcTileM) {
+        ptx::mbar_arrive_expect_tx(raw_full, (uint32_t)kTcRawStageBytes);
+        ptx::bulk_g2s(s_raw, a.raw + row0, (uint32_t)kTcRawStageBytes, raw_full);
+      } else {
+        ptx::mbar_arrive(raw_full);          // ragged last tile: the pool reads global memory directly
+      }
+    };
+    if (s < n_local && ptx::elect_one_sync()) {
+      load_tile(s);
+      if (kFused && s == 0) load_raw(0);
+    }
     __syncwarp();
     int phi = 0;
     for (int i = s; i < n_local; i += 2, phi ^= 1) {
@@ -376,6 +397,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
           ptx::tc_fence_after();
           if (ptx::elect_one_sync()) {
             if (i + 2 < n_local) load_tile(i + 2);
+            if (kFused && i + 1 < n_local) load_raw(i + 1);
             TC_TRACE(0x200u | (uint32_t)(l << 4) | (uint32_t)s);
             const int ksteps = kp / 16;      // A chunk j sits at 32*(j/2) + 8*(j%2), ones inside the data
             for (int j = 0; j < ksteps; ++j)
@@ -442,11 +464,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
         // back to the caller's history buffer with one bulk copy per lane quarter while the layers run
         float* srow = reinterpret_cast<float*>(stage0 + s * stage_bytes) + (size_t)m * a.in_dim;
         const bool full = valid == kTcTileM;
+        ptx::mbar_wait(raw_full, (uint32_t)(s & 1));       // CTA-local tile i = 2*pair + s: phase i & 1
         if (m < valid) {
           int lo, hi;
           tc_term_range(cb, a.H, lo, hi);
           if (!full) for (int k = lo; k < hi; ++k) srow[k] = a.obs_rw[(row0 + m) * a.in_dim + k];   // ragged tile: no bulk load
-          tc_update_terms(a, cb, srow, row0 + m, &s_button[(s * 2 + (pair & 1)) * kTcTileM + m]);
+          const uint32_t* rw = full ? s_raw + m * kTcRawWords : reinterpret_cast<const uint32_t*>(a.raw + row0 + m);
+          tc_update_terms(a, cb, srow, rw, row0 + m, &s_button[(s * 2 + (pair & 1)) * kTcTileM + m]);
           if (!full) for (int k = lo; k < hi; ++k) a.obs_rw[(row0 + m) * a.in_dim + k] = srow[k];
         }
         ptx::fence_proxy_async_smem();
@@ -565,6 +589,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
           const long long r1 = r0 + (long long)gridDim.x * kTcTileM;
           b0_s0 = r0 < a.B ? __ldg(a.button0 + r0) : 0;
           b0_s1 = r1 < a.B ? __ldg(a.button0 + r1) : 0;
+        }
+        if constexpr (kFused) {
+          if (l == 0) {
+            // the next pair's conversion jobs read these robots' raw states and previous actions: pull them into L2 now,
+            // two layers ahead (no registers held, nothing waited for)
+            const long long r0 = (blockIdx.x + (long long)(pair * 2 + 2 + (cb & 1)) * gridDim.x) * kTcTileM + m;
+            if (r0 < a.B) {
+              if (cb < 2) { ptx::prefetch_l2(a.raw + r0); ptx::prefetch_l2(reinterpret_cast<const uint8_t*>(a.raw + r0) + sizeof(RawStateDev) - 1); }
+              else { ptx::prefetch_l2(a.act + r0 * kDof); ptx::prefetch_l2(a.vel_cmd + r0 * 3); }
+            }
+          }
         }
         for (int s = 0; s < ns; ++s) {
           const uint32_t d_t = tmem_base + (uint32_t)s * kTcSlotCols + lane_addr + 128u * (uint32_t)((phi + 1 + l) & 1) + (uint32_t)(cb * 32);

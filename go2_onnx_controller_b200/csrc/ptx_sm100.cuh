@@ -24,6 +24,9 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// fire-and-forget: bring the line holding p into L2
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ------------------------------------------------------------------ programmatic dependent launch
 // wait: the grids this launch depends on (the previous kernel of the stream) have completed and their memory is visible
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
