@@ -199,6 +199,12 @@ class PolicyBatch:
         capi.check(self._hd.lib.go2p_infer_batch_host(self._hd.h, obs.ctypes.data, act.ctypes.data, obs.shape[0], precision))
         return act
 
+    def saturation_count(self, reset: bool = True, stream: int = 0) -> int:
+        """(row, operand block) pairs clipped at +-65504 by fp16 launches made with F_SAT_COUNT since the last reset."""
+        n = C.c_uint64()
+        capi.check(self._hd.lib.go2p_saturation_count(self._hd.h, C.byref(n), int(reset), stream or None))
+        return int(n.value)
+
     def last_launches(self) -> int:
         return int(self._hd.lib.go2p_last_launch_count(self._hd.h))
 

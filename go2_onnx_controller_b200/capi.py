@@ -14,7 +14,7 @@ GO2P_MAX_LAYERS = 8
 OK, ERR_INVALID, ERR_IO, ERR_MODEL, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_STATE, ERR_TIMEOUT = range(9)
 PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
 B1_PERSISTENT, B1_GRAPH, B1_LAUNCH = 0, 1, 2
-F_CLAMP_MASK, F_QDES, F_MOTOR_CMD = 1, 2, 4
+F_CLAMP_MASK, F_QDES, F_MOTOR_CMD, F_SAT_COUNT = 1, 2, 4, 8
 
 PREC_NAMES = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16}
 
@@ -93,6 +93,7 @@ SIGNATURES = {
     "go2p_step_batch": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                   C.c_void_p]),
     "go2p_last_launch_count": (C.c_int, [_H]),
+    "go2p_saturation_count": (C.c_int, [_H, C.POINTER(C.c_uint64), C.c_int, C.c_void_p]),
     "go2p_infer_batch_cmd": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                         C.c_uint32, C.c_void_p]),
     "go2p_step_batch_cmd": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,

@@ -105,6 +105,7 @@ struct go2p_handle {
   float* pipe_in[kPipeDepth] = {};
   float* pipe_out[kPipeDepth] = {};
   int last_launches = 0;
+  unsigned long long* d_sat = nullptr;         // GO2P_F_SAT_COUNT: saturated fp16 operand blocks since the last read
   // ObservationAction ring (go2p_log_enable)
   LogRing* d_log = nullptr;
   uint32_t log_capacity = 0;
@@ -406,6 +407,9 @@ int ensure_scratch(go2p_handle* h, int64_t rows) {
 int launch_fp32(go2p_handle* h, const float* d_obs, const int32_t* d_button0, float* d_act, double* d_qdes,
                 MotorCmdDev* d_cmd, int64_t B, uint32_t flags, cudaStream_t st) {
   const DevModel& dm = h->dm;
+  // the GEMM epilogue stores float4 where the row pitch allows it: the output base has to be 16-byte aligned
+  if ((reinterpret_cast<uintptr_t>(d_act) & 15) || (d_qdes && (reinterpret_cast<uintptr_t>(d_qdes) & 15)))
+    return fail(GO2P_ERR_INVALID, "fp32 path needs 16-byte aligned act/qdes device pointers");
   const int64_t chunk = std::min<int64_t>(B, kFp32ChunkRows);
   int rc = ensure_scratch(h, chunk);
   if (rc) return rc;
@@ -488,6 +492,14 @@ int launch_tc(go2p_handle* h, const float* d_obs, const int32_t* d_button0, floa
   TcArgs a{};
   a.obs = d_obs; a.act = d_act; a.button0 = d_button0; a.qdes = d_qdes; a.B = B;
   a.cmd = d_cmd; a.kp = h->cc.kp; a.kd = h->cc.kd; a.kp_deadman = h->cc.kp_deadman;
+  a.sat_count = nullptr;
+  if (flags & GO2P_F_SAT_COUNT) {
+    if (!h->d_sat) {
+      CU_TRY(cudaMalloc((void**)&h->d_sat, sizeof(unsigned long long)));
+      CU_TRY(cudaMemsetAsync(h->d_sat, 0, sizeof(unsigned long long), st));
+    }
+    a.sat_count = h->d_sat;
+  }
   a.wpack = h->d_wpack[fp16 ? 1 : 0];
   a.n_layers = h->dm.n_layers; a.in_dim = h->dm.in_dim; a.k0p = h->k0p; a.out_dim = h->dm.out_dim;
   for (int l = 0; l < h->dm.n_layers; ++l) {
@@ -657,6 +669,7 @@ int go2p_destroy(go2p_handle* h) {
   if (h->d_state) cudaFree(h->d_state);
   if (h->d_step_button) cudaFree(h->d_step_button);
   if (h->d_log) cudaFree(h->d_log);
+  if (h->d_sat) cudaFree(h->d_sat);
   for (void* p : {(void*)h->fleet.obs, (void*)h->fleet.vel, (void*)h->fleet.act}) if (p) cudaFree(p);
   for (int i = 0; i < kPipeDepth; ++i) {
     if (h->fleet.raw[i]) cudaFree(h->fleet.raw[i]);
@@ -976,6 +989,22 @@ int go2p_infer_batch(go2p_handle* h, const float* d_obs, float* d_act, int64_t B
 }
 
 int go2p_last_launch_count(const go2p_handle* h) { return h ? h->last_launches : 0; }
+
+// GO2P_F_SAT_COUNT: (row, 32-column operand block) pairs with a saturated fp16 operand in the launches since the last
+// reset, read after `stream` has drained
+int go2p_saturation_count(go2p_handle* h, uint64_t* count, int reset, void* stream) {
+  if (!h || !count) return fail(GO2P_ERR_INVALID, "go2p_saturation_count: null argument");
+  *count = 0;
+  if (!h->d_sat) return GO2P_OK;                       // no counting launch yet
+  DeviceGuard g(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned long long v = 0;
+  CU_TRY(cudaMemcpyAsync(&v, h->d_sat, sizeof(v), cudaMemcpyDeviceToHost, st));
+  if (reset) CU_TRY(cudaMemsetAsync(h->d_sat, 0, sizeof(v), st));
+  CU_TRY(cudaStreamSynchronize(st));
+  *count = v;
+  return GO2P_OK;
+}
 
 // Isaac joint index of every Unitree motor (controller.hpp:168-170 vs the SDK's FR, FL, RR, RL x hip, thigh, calf)
 int go2p_motor_order(int32_t isaac_of_motor[GO2P_DOF]) {

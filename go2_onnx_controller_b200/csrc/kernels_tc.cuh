@@ -62,6 +62,10 @@ struct TcArgs {
   double q0[kDof];
   MotorCmdDev* cmd;          // [B] send_command arguments in Unitree motor order (flag 4) or null
   float kp, kd, kp_deadman;
+  // fp16 operands saturate at +-65504 where the fp32 reference does not (cvt.rn.satfinite): with flag 8 the kernel counts,
+  // per launch, the (row, 32-column operand block) pairs in which at least one packed operand -- an observation or a
+  // hidden activation -- sits at the largest finite magnitude.  0 = no operand was clipped on the way.
+  unsigned long long* sat_count;
   // fused controller step (go2p_step_batch, tc_mlp_kernel<., true>): A1-A6 run in the conversion job.  obs_rw holds
   // every robot's history (== its previous observation) and is updated in place; act holds the previous published
   // action on entry (read by the assembly) and the new one on return; button0 comes from the raw state.
@@ -102,6 +106,16 @@ constexpr int kTcRawWords = 39;                               // sizeof(RawState
 constexpr int kTcRawStageBytes = kTcTileM * kTcRawWords * 4;    // fused step: one tile's raw states (128 x 156 B, contiguous)
 __host__ __device__ inline size_t tc_smem_bytes(const TcArgs& a) {
   return tc_weight_bytes(a) + 2 * tc_stage_bytes(a) + 256 + 4 * kTcTileM * 4 + (a.raw ? kTcRawStageBytes : 0);
+}
+
+// does any half of these packed fp16 words sit at the largest finite magnitude (0x7BFF)?  (h & 0x7FFF) + 0x0401 reaches
+// bit 15 exactly then (satfinite conversion never produces Inf; NaN payloads, 0x7C01.., are reported as well)
+template <int kN>
+__device__ __forceinline__ bool any_saturated_f16x2(const uint32_t (&w)[kN]) {
+  uint32_t t = 0u;
+#pragma unroll
+  for (int j = 0; j < kN; ++j) t |= (w[j] & 0x7FFF7FFFu) + 0x04010401u;
+  return (t & 0x80008000u) != 0u;
 }
 
 // ---- fused A1-A6: history shift + newest frame of one observation term, in place in the row's shared-memory copy
@@ -446,6 +460,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
     const bool even = (a.in_dim & 1) == 0;
 
     uint32_t par_acc[2] = {0u, 0u};
+    uint32_t n_sat = 0u;                     // flag 8: (row, operand block) pairs with a saturated fp16 operand seen by this thread
     const bool masked = (a.flags & 5u) && a.button0 != nullptr;   // the clamp/mask and the kp selection read the button
     int b0_s0 = 0, b0_s1 = 0;                // dead-man buttons of this thread's row in the two slots' tiles
     // ---- conv(s): fp32 observation rows -> 16-bit layer-0 A operand, constant ones at K = in_dim, in_dim+1.
@@ -458,6 +473,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
       ptx::mbar_wait(&obs_full[s], (uint32_t)(pair & 1));
       TC_TRACE(0x400u | (uint32_t)s);
       const int c8_hi = min(n8, 2 * cb + 2);
+      bool conv_sat = false;
       if constexpr (kFused) {
         // ---- A1-A6 (controller.cpp:173-212): the stage holds the tile's previous observations (== histories);
         // shift them by one frame and append the newest frame from the raw states, in place, then send the rows
@@ -498,7 +514,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
             }
           }
           ptx::tmem_st_x8(a0_t + (uint32_t)(32 * (c8 >> 1) + 8 * (c8 & 1)), q);
+          if (kFp16 && a.sat_count && m < valid) conv_sat = conv_sat || any_saturated_f16x2(q);
         }
+        n_sat += conv_sat ? 1u : 0u;
       } else {
         const float* rowp = (valid == kTcTileM || kFused) ? reinterpret_cast<const float*>(stage0 + s * stage_bytes) + (size_t)m * a.in_dim
                                                           : a.obs + (row0 + m) * a.in_dim;
@@ -620,9 +638,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
           elu_pack16<kFp16>(cur, he, c, pk);
           TC_TRACE(0xF00u | (2u << 4) | (uint32_t)s);
           ptx::tmem_st_x8(d_t, pk);
+          bool sat = kFp16 && a.sat_count && any_saturated_f16x2(pk);
           elu_pack16<kFp16>(nxt, he, c, pk);
           TC_TRACE(0xF00u | (3u << 4) | (uint32_t)s);
           ptx::tmem_st_x8(d_t + 8u, pk);
+          if (kFp16 && a.sat_count) n_sat += (sat || any_saturated_f16x2(pk)) ? 1u : 0u;
           if (cb == 0) {   // constant-one columns (K = 128,129; zeros up to 143) in the dead half of block 0
             const uint32_t ones[8] = {one2, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
             ptx::tmem_st_x8(d_t + 16u, ones);
@@ -648,6 +668,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
         }
         if (s < ns_next) conv_job(pair + 1, s);
       }
+    }
+    if (kFp16 && a.sat_count) {
+      uint32_t n = n_sat;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+      if (lane == 0 && n) atomicAdd(a.sat_count, (unsigned long long)n);
     }
   }
 

@@ -68,6 +68,7 @@ typedef enum go2p_b1_mode {
 #define GO2P_F_CLAMP_MASK 1u   /* apply A9 (clamp to +-action_limit, multiply by button0==0) */
 #define GO2P_F_QDES 2u         /* also emit A11 q_des = q0 + (double)a * action_scale        */
 #define GO2P_F_MOTOR_CMD 4u    /* also emit the send_command arguments in Unitree motor order (go2p_motor_cmd) */
+#define GO2P_F_SAT_COUNT 8u    /* GO2P_PREC_FP16 only: count operand blocks clipped at +-65504 (go2p_saturation_count) */
 
 /* Compile-time constants of the reference exposed as one POD; go2p_config_default()
  * fills in the reference's values. */
@@ -223,6 +224,11 @@ int go2p_motor_order(int32_t isaac_of_motor[GO2P_DOF]);
 int go2p_step_batch_host(go2p_handle* h, const go2p_raw_state* h_raw, float* h_action, go2p_motor_cmd* h_cmd,
                          int64_t B, int precision);
 int go2p_step_batch_host_reset(go2p_handle* h);
+/* fp16 operands saturate at +-65504 where the fp32 reference does not.  Launches with GO2P_F_SAT_COUNT count the
+ * (row, 32-column operand block) pairs in which an observation or a hidden activation was clipped on its way into a
+ * Gemm; this reads (and optionally resets) the total once `stream` has drained.  0 means the fp16 path never left the
+ * reference's range; otherwise use GO2P_PREC_FP32 (or bf16, which has the fp32 range) for those inputs. */
+int go2p_saturation_count(go2p_handle* h, uint64_t* count, int reset, void* stream);
 /* number of kernels the previous batched call launched (for bench.py's gpu_launches) */
 int go2p_last_launch_count(const go2p_handle* h);
 

@@ -272,3 +272,68 @@ def test_relu_policy_with_observation_normaliser_all_paths(torch_cuda, tmp_path)
             assert (np.abs(act - ref[i]) / np.maximum(1, np.abs(ref[i]))).max() <= 1e-5
     finally:
         a.close()
+
+
+def _scaled_operands(pol, X):
+    """The fp16 kernel's Gemm operands in its own (base-2 exponent) domain: the observation, then every hidden
+    activation h' = log2(e) * elu(z), fp64 evaluation -- what cvt.rn.satfinite.f16x2 sees, up to rounding."""
+    ops = [X.astype(np.float64)]
+    h = X.astype(np.float64)
+    with np.errstate(over="ignore", invalid="ignore"):
+        for layer in pol.layers[:-1]:
+            z = h @ layer.weight.astype(np.float64).T + layer.bias.astype(np.float64)
+            h = oracle.elu(z, layer.elu_alpha)
+            ops.append(h * np.log2(np.e))
+    return ops
+
+
+def test_fp16_saturation_is_counted_and_clean_rows_clip_like_the_reference(torch_cuda, model_path, golden, policy):
+    """fp16 operands saturate at +-65504 where the fp32 reference does not (the x3000 stress set D3 reaches 1e6).
+    GO2P_F_SAT_COUNT reports how many (row, 32-column operand block) pairs were clipped; on the rows the oracle
+    predicts clean, the clip / mask decisions (controller.cpp:217-223) are the reference's."""
+    torch = torch_cuda
+    pb = PolicyBatch(model_path)
+    try:
+        # realistic observations never saturate: the counter stays at zero
+        X2 = golden["d2_obs"]
+        d_obs = torch.from_numpy(X2).cuda(); d_act = torch.zeros((X2.shape[0], 12), device="cuda")
+        pb.infer_device(d_obs.data_ptr(), d_act.data_ptr(), X2.shape[0], capi.PREC_FP16, 0, None, None, capi.F_SAT_COUNT)
+        assert pb.saturation_count() == 0
+        # stress set x4 (its own activations stay below 31k): finite rows only -- NaN / Inf rows are covered by the
+        # NaN-propagation test.  An operand block certainly saturates if it exceeds the format in the FIRST stage where
+        # the row saturates at all (everything upstream of it is then exactly what the oracle predicts).
+        X, b0 = golden["d3_obs"], golden["d3_button0"]
+        fin = np.isfinite(X).all(axis=1)
+        X, b0 = np.ascontiguousarray(X[fin] * np.float32(4.0)), np.ascontiguousarray(b0[fin])
+        ops = _scaled_operands(policy, X)
+        clean = np.ones(X.shape[0], bool)
+        undecided = np.ones(X.shape[0], bool)          # rows not yet saturated in an earlier stage
+        certain = 0
+        for o in ops:
+            pad = np.zeros((o.shape[0], 128)); pad[:, : o.shape[1]] = np.abs(o)
+            blk = pad.reshape(o.shape[0], 4, 32).max(axis=2)          # per (row, 32-column block)
+            certain += int((blk[undecided] > 66000).sum())
+            undecided &= (blk < 65000).all(axis=1)
+            clean &= (blk < 60000).all(axis=1)
+        assert certain > 50 and clean.sum() > 20, (certain, clean.sum())
+        d_obs = torch.from_numpy(X).cuda(); d_act = torch.zeros((X.shape[0], 12), device="cuda")
+        d_b = torch.from_numpy(b0.astype(np.int32)).cuda()
+        pb.infer_device(d_obs.data_ptr(), d_act.data_ptr(), X.shape[0], capi.PREC_FP16, 0, d_b.data_ptr(), None,
+                        capi.F_CLAMP_MASK | capi.F_SAT_COUNT)
+        n = pb.saturation_count()
+        assert certain <= n <= int((~clean).sum()) * 16, (certain, n)
+        assert pb.saturation_count() == 0                             # reading resets
+        # the clean rows alone: nothing is counted
+        Xc = np.ascontiguousarray(X[clean]); d_c = torch.from_numpy(Xc).cuda(); d_ac = torch.zeros((Xc.shape[0], 12), device="cuda")
+        pb.infer_device(d_c.data_ptr(), d_ac.data_ptr(), Xc.shape[0], capi.PREC_FP16, 0, None, None, capi.F_SAT_COUNT)
+        assert pb.saturation_count() == 0
+        # rows without any clipped operand: same clip / mask decisions as the fp64 oracle, away from the clip edge
+        got = d_act.cpu().numpy()[clean]
+        ref = oracle.forward(policy, X[clean])
+        exp = oracle.clamp_mask(ref.astype(np.float32), b0[clean][:, None])
+        decided = (np.abs(np.abs(ref) - 1000) > 50.0)
+        assert np.array_equal(np.abs(got[decided]) == 1000, np.abs(exp[decided]) == 1000)
+        assert np.array_equal(got[decided] == 0, exp[decided] == 0)
+        assert np.array_equal(np.signbit(got[decided]), np.signbit(exp[decided]))
+    finally:
+        pb.close()
