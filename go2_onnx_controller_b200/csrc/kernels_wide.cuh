@@ -100,6 +100,9 @@ template <bool kFp16>
 __global__ void obs_to_blocked_kernel(const float* __restrict__ obs, uint16_t* __restrict__ out, long long B, int in_dim, int Kp,
                                       long long m_tiles) {
   const long long groups = m_tiles * kWdTileM * (Kp / 8);          // one thread per (row, 8-column group)
+  // programmatic dependent launch: the previous pass may still be reading the buffer this kernel rewrites
+  ptx::grid_dependency_wait();
+  ptx::grid_launch_dependents();
   for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < groups; gidx += (long long)gridDim.x * blockDim.x) {
     const int kg = (int)(gidx % (Kp / 8));
     const long long row = gidx / (Kp / 8);
@@ -166,6 +169,12 @@ __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemm
   if (kCS > 1) ptx::cluster_sync_all();     // the peer's barriers exist before anything is multicast into them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // Programmatic dependent launch: barriers and TMEM are set up while the previous layer's launch drains; its
+  // activations are read (and the buffer two layers back is overwritten) only after that launch has completed.  The
+  // next layer's launch may begin its own set-up as soon as this CTA's SM is free.  (5 launches per 18,944-row pass:
+  // the gaps between them were a quarter of the wide policy's time.)
+  ptx::grid_dependency_wait();
+  ptx::grid_launch_dependents();
 
   // job = (group of kCS row tiles, N tile), N tile fastest: the A tiles stay in L2 for the next N tile.
   // Every CTA of a cluster walks the same job list; CTA rank r takes row tile group*kCS + r.  A rank whose row tile
@@ -414,14 +423,17 @@ inline cudaError_t wd_launch_gemm(const WideGemmArgs& a, int sm_count, cudaStrea
   int dev = 0;
   cudaGetDevice(&dev);
   cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   cfg.blockDim = dim3(kWdThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // see griddepcontrol.wait in the kernel
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
   if (kCS > 1) {
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kCS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = kCS; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
   }
   if (configured_dev != dev) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -477,8 +489,16 @@ inline int wide_launch(const WideModel& wm, const float* d_obs, const int32_t* d
     {
       const long long groups = (long long)m_tiles * kWdTileM * (L0.Kp / 8);
       const int blocks = (int)std::min<long long>((groups + 255) / 256, (long long)sm_count * 8);
-      if (fp16) obs_to_blocked_kernel<true><<<blocks, 256, 0, st>>>(d_obs + r0 * wm.in_dim, act[0], rows, wm.in_dim, L0.Kp, m_tiles);
-      else obs_to_blocked_kernel<false><<<blocks, 256, 0, st>>>(d_obs + r0 * wm.in_dim, act[0], rows, wm.in_dim, L0.Kp, m_tiles);
+      cudaLaunchConfig_t lc = {};
+      cudaLaunchAttribute la;
+      la.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      la.val.programmaticStreamSerializationAllowed = 1;
+      lc.gridDim = dim3((unsigned)blocks); lc.blockDim = dim3(256); lc.stream = st; lc.attrs = &la; lc.numAttrs = 1;
+      const float* src = d_obs + r0 * wm.in_dim;
+      const long long m_tiles_ll = m_tiles;
+      cudaError_t ec = fp16 ? cudaLaunchKernelEx(&lc, obs_to_blocked_kernel<true>, src, act[0], rows, wm.in_dim, L0.Kp, m_tiles_ll)
+                            : cudaLaunchKernelEx(&lc, obs_to_blocked_kernel<false>, src, act[0], rows, wm.in_dim, L0.Kp, m_tiles_ll);
+      if (ec != cudaSuccess) { err = std::string("wide_launch: ") + cudaGetErrorString(ec); return 4; }
       ++*launches;
     }
     int cur = 0;
