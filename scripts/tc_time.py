@@ -7,12 +7,20 @@ import go2_onnx_controller_b200 as pkg
 from go2_onnx_controller_b200 import capi
 from oracle import oracle
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 1_048_576
-pb = pkg.PolicyBatch(pkg.DEFAULT_MODEL)
+model, width = pkg.DEFAULT_MODEL, 98
+if os.environ.get("GO2P_TIME_IN"):      # synthetic Go2-topology policy with another input width
+    import tempfile
+    from go2_onnx_controller_b200 import onnx_writer
+    width = int(os.environ["GO2P_TIME_IN"])
+    ws, bs = onnx_writer.wide_policy(seed=3, dims=(width, 128, 128, 128, 12))
+    model = os.path.join(tempfile.mkdtemp(), "narrow.onnx")
+    onnx_writer.write_policy(model, ws, bs)
+pb = pkg.PolicyBatch(model)
 g = torch.Generator(device="cuda").manual_seed(0)
-obs = torch.randn((rows, 98), device="cuda", generator=g)
+obs = torch.randn((rows, width), device="cuda", generator=g)
 act = torch.zeros((rows, 12), device="cuda")
 b0 = torch.zeros(rows, device="cuda", dtype=torch.int32)
-pol = oracle.load_policy(pkg.DEFAULT_MODEL)
+pol = oracle.load_policy(model)
 def timed(fn, n=20):
     for _ in range(3): fn()
     torch.cuda.synchronize()
@@ -28,4 +36,4 @@ for name, prec in (("fp16", capi.PREC_FP16), ("bf16", capi.PREC_BF16)):
     ref = oracle.forward(pol, obs[idx].cpu().numpy())
     err = float(np.abs(act[idx].cpu().numpy() - ref).max())
     print(f"{os.path.basename(os.environ.get('GO2P_LIB', 'libgo2policy.so'))} {name}: plain {t0:.4f} ms  clamp {t1:.4f} ms  "
-          f"frac {440 * rows / (t1 * 1e-3) / 6455.6e9:.3f}  err {err:.2e}")
+          f"frac {(4 * width + 48) * rows / (t1 * 1e-3) / 6455.6e9:.3f}  err {err:.2e}")

@@ -13,8 +13,16 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 1_048_576
 lo = int(sys.argv[2]) if len(sys.argv) > 2 else 320
 cnt = int(sys.argv[3]) if len(sys.argv) > 3 else 64
 warps = [int(w) for w in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0, 16]
-pb = pkg.PolicyBatch(pkg.DEFAULT_MODEL)
-d_obs = torch.randn((B, 98), device="cuda"); d_act = torch.empty((B, 12), device="cuda")
+model, width = pkg.DEFAULT_MODEL, 98
+if os.environ.get("GO2P_TIME_IN"):      # synthetic Go2-topology policy with another input width
+    import tempfile
+    from go2_onnx_controller_b200 import onnx_writer
+    width = int(os.environ["GO2P_TIME_IN"])
+    ws, bs = onnx_writer.wide_policy(seed=3, dims=(width, 128, 128, 128, 12))
+    model = os.path.join(tempfile.mkdtemp(), "narrow.onnx")
+    onnx_writer.write_policy(model, ws, bs)
+pb = pkg.PolicyBatch(model)
+d_obs = torch.randn((B, width), device="cuda"); d_act = torch.empty((B, 12), device="cuda")
 for _ in range(3):
     trace.zero_()
     torch.cuda.synchronize()
