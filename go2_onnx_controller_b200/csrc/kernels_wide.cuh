@@ -464,9 +464,16 @@ inline void wide_release(WideModel* wm) {
   wm->retired.clear();
 }
 
-// rows per pass: 148 row tiles, so every layer's job count is a whole number of waves over the 148 SMs, and the widest
-// activation (18944 x 1024 x 2 B = 39 MB) still stays in the 126 MB L2 together with the next layer's output
-constexpr long long kWdChunkRows = 148 * kWdTileM;
+// rows per pass: a multiple of 148 row tiles, so every layer's job count is a whole number of waves over the 148 SMs.
+// Round 1 used ONE wave of row tiles (18,944 rows: the widest activation, 39 MB, stays in the 126 MB L2); measured in
+// round 2 (scripts/gpu_wide_variants.sh, 606,208 rows, fp16 / bf16): 1 wave 1.86 / 1.85 ms, 2 waves 1.62 / 1.66 ms,
+// 4 waves 1.57 / 1.51 ms, 32 waves (the whole batch) 1.54 / 1.48 ms -- the five launches per pass each end in a tail
+// (layers 3 and 4 are ONE job per CTA at one wave: no overlap of epilogue and MMAs at all), and that costs more than
+// reading the activations back from HBM instead of L2.  Four waves: 75,776 rows, 155 MB per activation buffer.
+#ifndef GO2P_WD_PASS_WAVES
+#define GO2P_WD_PASS_WAVES 4
+#endif
+constexpr long long kWdChunkRows = 148 * kWdTileM * GO2P_WD_PASS_WAVES;
 
 inline int wide_launch(const WideModel& wm, const float* d_obs, const int32_t* d_button0, float* d_act, double* d_qdes, MotorCmdDev* d_cmd, long long B,
                        bool fp16, uint32_t flags, const CtrlConst& cc, int sm_count, cudaStream_t st, int* launches, std::string& err, int set = 0) {

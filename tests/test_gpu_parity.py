@@ -529,14 +529,14 @@ def test_wide_policy_fp32_path(torch_cuda, wide_model_path):
 @pytest.mark.parametrize("prec", [capi.PREC_FP16, capi.PREC_BF16])
 def test_wide_policy_tensor_core_path(torch_cuda, wide_model_path, prec):
     """configs[4] on the per-layer tcgen05 GEMM kernels (kernels_wide.cuh): ragged batches, a batch larger than one
-    L2-resident pass (148 row tiles = 18944 rows), the fused A9/A11 epilogue, and the host-buffer pipeline (concurrent streams)."""
+    pass (4 x 148 row tiles = 75,776 rows), the fused A9/A11 epilogue, and the host-buffer pipeline (concurrent streams)."""
     cm = coracle.CModel(wide_model_path)
     p = PolicyBatch(wide_model_path, history=5)
     tol = 2e-2 if prec == capi.PREC_FP16 else 1.2e-1
     try:
         assert p.info.tensor_core_path == 1
-        CH = 148 * 128
-        for B in (1, 129, 3001, 2 * CH + 77):
+        CH = 4 * 148 * 128
+        for B in (1, 129, 3001, CH + 77):
             X = oracle.make_obs_d1(B, 245, seed=B)
             ref = cm.forward_f64(X, 8)
             y, _ = run_batch(torch_cuda, p, X, prec)
