@@ -24,8 +24,9 @@
 //     h' = z' > 0 ? z' : c*(2^z' - 1) with c = alpha*log2(e), h' = log2(e)*h feeds the next layer whose weights
 //     carry the inverse factor (folded on the host);
 //   * fp16 path: the ELU runs on packed pairs -- F2FP (pack z'), ex2.approx.f16x2 (2 MUFU + PRMT), one HFMA2
-//     (c*e - c), HSET2 + LOP3 select: 7 instructions per pair; one pair in eight takes a polynomial 2^x on the FMA
-//     pipe instead of the MUFU (16 lanes/clk/SM).  bf16 keeps the fp32 exponential;
+//     (c*e - c), HSET2 + LOP3 select: 7 instructions per pair; two pairs in eight take a packed-half polynomial
+//     2^x on the FMA pipe instead (elu_neg_poly_f16x2): the MUFU (4 lanes/clk per scheduler, an ex2.f16x2 is two
+//     MUFU.EX2.F16) is what an epilogue job saturates.  bf16 keeps the fp32 exponential;
 //   * one elected thread issues every tcgen05.mma and signals completion with tcgen05.commit; ONE pool of 16 worker
 //     warps walks the jobs of both slots alternately, so a slot's MMAs run while the pool works on the other slot.
 #pragma once
