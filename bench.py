@@ -41,7 +41,7 @@ WIDE_FLOP_PER_INF = 2 * (245 * 1024 + 1024 * 512 + 512 * 256 + 256 * 12)
 RAW_BYTES = 156                               # sizeof(go2p_raw_state)
 # dram__bytes_read.sum + dram__bytes_write.sum of one tc_mlp_kernel launch over 1,048,576 rows, from the ncu --set full
 # capture of the shipped kernel (profiles/r02_tc_mlp_kernel_raw.csv)
-NCU_TRAFFIC_BYTES_PER_ROW = (415.561984e6 + 44.075008e6) / 1048576
+NCU_TRAFFIC_BYTES_PER_ROW = (415.403520e6 + 41.018112e6) / 1048576
 L2_BYTES = 126e6
 METRIC = "policy_inferences_per_sec"
 UNIT = "inferences/s"
