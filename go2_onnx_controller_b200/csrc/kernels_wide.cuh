@@ -292,7 +292,13 @@ __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemm
           uint32_t v[32];
           ptx::tmem_ld_x32(acc_t + (uint32_t)c0, v);
           ptx::tc_wait_ld();
-          const float* bl = a.bias + nt * NT + c0;
+          // the 32 biases of this column group as eight 16-byte loads (warp-uniform address, 128-byte aligned)
+          float bl[32];
+          {
+            const float4* b4 = reinterpret_cast<const float4*>(a.bias + nt * NT + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float4 t = __ldg(b4 + j); bl[4 * j] = t.x; bl[4 * j + 1] = t.y; bl[4 * j + 2] = t.z; bl[4 * j + 3] = t.w; }
+          }
           uint32_t p[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
