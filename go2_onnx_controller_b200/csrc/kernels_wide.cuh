@@ -300,17 +300,27 @@ __global__ void __launch_bounds__(kWdThreads, 1) wide_gemm_kernel(const WideGemm
             for (int j = 0; j < 8; ++j) { const float4 t = __ldg(b4 + j); bl[4 * j] = t.x; bl[4 * j + 1] = t.y; bl[4 * j + 2] = t.z; bl[4 * j + 3] = t.w; }
           }
           uint32_t p[16];
+          // the activation test is hoisted out of the unrolled loop: inside it nvcc emitted a branch with its
+          // reconvergence bookkeeping and a constant-bank reload of alpha per PAIR (15+ instead of 11 instructions)
+          if (a.has_elu) {
+            const float alpha = a.alpha, nalpha = -a.alpha;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float x0 = __uint_as_float(v[2 * j]) + bl[2 * j];
-            float x1 = __uint_as_float(v[2 * j + 1]) + bl[2 * j + 1];
-            if (a.has_elu) {
-              const float e0 = fmaf(a.alpha, ptx::ex2_approx(x0 * 1.4426950408889634f), -a.alpha);
-              const float e1 = fmaf(a.alpha, ptx::ex2_approx(x1 * 1.4426950408889634f), -a.alpha);
+            for (int j = 0; j < 16; ++j) {
+              float x0 = __uint_as_float(v[2 * j]) + bl[2 * j];
+              float x1 = __uint_as_float(v[2 * j + 1]) + bl[2 * j + 1];
+              const float e0 = fmaf(alpha, ptx::ex2_approx(x0 * 1.4426950408889634f), nalpha);
+              const float e1 = fmaf(alpha, ptx::ex2_approx(x1 * 1.4426950408889634f), nalpha);
               x0 = (x0 < 0.f) ? e0 : x0;
               x1 = (x1 < 0.f) ? e1 : x1;
+              p[j] = kFp16 ? ptx::pack_f16_sat(x0, x1) : ptx::pack_bf16(x0, x1);
             }
-            p[j] = kFp16 ? ptx::pack_f16_sat(x0, x1) : ptx::pack_bf16(x0, x1);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float x0 = __uint_as_float(v[2 * j]) + bl[2 * j];
+              const float x1 = __uint_as_float(v[2 * j + 1]) + bl[2 * j + 1];
+              p[j] = kFp16 ? ptx::pack_f16_sat(x0, x1) : ptx::pack_bf16(x0, x1);
+            }
           }
           const int kn = nt * NT + c0;                 // K index of the next layer
           uint8_t* dst = reinterpret_cast<uint8_t*>(a.out_blocked) + ((mt * next_chunks + kn / kWdChunkK) * (long long)kWdATileBytes) +
