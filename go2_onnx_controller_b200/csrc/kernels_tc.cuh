@@ -210,6 +210,9 @@ __device__ __forceinline__ uint32_t elu_neg_poly_f16x2(uint32_t z, uint32_t ch2,
 // same on 16 accumulator columns -> 8 packed words.  fp16: every pair stays packed -- F2FP (pack z'), then either
 // ex2.approx.f16x2 (2 MUFU + PRMT) + HFMA2 (c*e - c) or, for the pairs selected by GO2P_TC_POLYMASK, the FMA-pipe
 // polynomial above; HSET2 + LOP3 select.  bf16 keeps the fp32 exponential everywhere (its budget has no slack).
+#ifndef GO2P_TC_WARM_L2
+#define GO2P_TC_WARM_L2 1
+#endif
 #ifndef GO2P_TC_POLYMASK
 #define GO2P_TC_POLYMASK 0x88u     // bit j: column pair j of every 8 takes the FMA-pipe exponential (2 of 8)
 #endif
@@ -348,6 +351,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
   // change after go2p_create) may run while the previous kernel of the stream drains; observations are read and
   // actions written only after that kernel has completed.  The next launch may start its own prologue as soon as
   // this CTA's SM is free (a short batch per GPU, e.g. 1/8 of a sharded step, is otherwise launch-gap bound).
+#if GO2P_TC_WARM_L2
+  // While the previous kernel drains, pull this CTA's first two observation slabs into L2 (prefetch only: L2 is the
+  // point of coherence, so a line the previous kernel still rewrites is simply updated there).  Matters for short
+  // launches -- 1/8 of a sharded step is 7 tiles per CTA, and the first slab's HBM latency is part of every launch.
+  {
+    const long long tiles_all = (a.B + kTcTileM - 1) / kTcTileM;
+    const long long slab_lines = ((long long)kTcTileM * a.in_dim * 4 + 127) / 128;
+    for (int t = 0; t < 2; ++t) {
+      const long long tile = blockIdx.x + (long long)t * gridDim.x;
+      if (tile >= tiles_all) break;
+      const uint8_t* base = reinterpret_cast<const uint8_t*>(a.obs + tile * kTcTileM * a.in_dim);
+      const long long lim = min(slab_lines, (((a.B - tile * kTcTileM) * a.in_dim * 4) + 127) / 128);
+      for (long long i = tid; i < lim; i += blockDim.x) ptx::prefetch_l2(base + i * 128);
+    }
+  }
+#endif
   ptx::grid_dependency_wait();
   ptx::grid_launch_dependents();
 
