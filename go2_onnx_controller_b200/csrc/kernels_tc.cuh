@@ -135,7 +135,9 @@ __device__ __forceinline__ void tc_shift_append(float* term, int H, const float 
 // Column block cb of a lane quarter updates "its" terms of row `srow` (robot `grow`): cb 0 gravity / angular velocity /
 // joystick command, cb 1 joint positions, cb 2 joint velocities, cb 3 previous action / foot contacts (+ the dead-man
 // button for the output job).  Bit-exact rules as in kernels_b1.cuh (same device functions).
-__device__ __forceinline__ void tc_update_terms(const TcArgs& a, int cb, float* srow, const uint32_t* rw, long long grow, int* button_out) {
+// pa4 (cb 3) / vc (cb 0): the row's previous published action / last joystick command, loaded one job ahead.
+__device__ __forceinline__ void tc_update_terms(const TcArgs& a, int cb, float* srow, const uint32_t* rw, long long grow, int* button_out,
+                                                const float4 (&pa4)[3], const float (&vc)[3]) {
   const float* rf = reinterpret_cast<const float*>(rw);     // this robot's raw state: 39 words (shared-memory stage, or global for a ragged tile)
   const int H = a.H;
   if (cb == 0) {
@@ -150,7 +152,7 @@ __device__ __forceinline__ void tc_update_terms(const TcArgs& a, int cb, float* 
       for (int c = 0; c < 3; ++c) { cmd[c] = vel_cmd_component(axes, c); a.vel_cmd[grow * 3 + c] = cmd[c]; }
     } else {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) cmd[c] = a.vel_cmd[grow * 3 + c];
+      for (int c = 0; c < 3; ++c) cmd[c] = vc[c];
     }
     tc_shift_append<3>(srow, H, g);
     tc_shift_append<3>(srow + 3 * H, H, w);
@@ -166,10 +168,9 @@ __device__ __forceinline__ void tc_update_terms(const TcArgs& a, int cb, float* 
     for (int c = 0; c < kDof; ++c) dq[c] = rf[19 + c];
     tc_shift_append<kDof>(srow + 21 * H, H, dq);
   } else {
-    float pa[kDof];
-    const float4* p4 = reinterpret_cast<const float4*>(a.act + grow * kDof);      // previous published action
+    float pa[kDof];                                                               // previous published action
 #pragma unroll
-    for (int q = 0; q < 3; ++q) { const float4 t = p4[q]; pa[4 * q] = t.x; pa[4 * q + 1] = t.y; pa[4 * q + 2] = t.z; pa[4 * q + 3] = t.w; }
+    for (int q = 0; q < 3; ++q) { const float4 t = pa4[q]; pa[4 * q] = t.x; pa[4 * q + 1] = t.y; pa[4 * q + 2] = t.z; pa[4 * q + 3] = t.w; }
     float ct[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
           ptx::mbar_wait(&blk[0], par);
           ptx::tc_fence_after();
           if (ptx::elect_one_sync()) {
-            if (i + 2 < n_local) load_tile(i + 2);
+            if (!kFused && i + 2 < n_local) load_tile(i + 2);
             if (kFused && i + 1 < n_local) load_raw(i + 1);
             TC_TRACE(0x200u | (uint32_t)(l << 4) | (uint32_t)s);
             const int ksteps = kp / 16;      // A chunk j sits at 32*(j/2) + 8*(j%2), ones inside the data
@@ -438,6 +439,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
               ptx::mma_f16_ts(dst, src + (uint32_t)(32 * (j >> 1) + 8 * (j & 1)), bdesc0 + (uint64_t)(j * 16), idesc, j > 0 ? 1u : 0u);
             ptx::mma_commit(&acc_full[s]);
             TC_TRACE(0x300u | (uint32_t)(l << 4) | (uint32_t)s);
+            if constexpr (kFused) {
+              // fused step: the stage now holds the tile's UPDATED observation rows (every pool warp fenced its
+              // writes towards the async proxy before it signalled): send them back to the caller's history buffer
+              // with one bulk copy, and refill the stage only when the copy has read it.  This warp has ~3,000
+              // cycles until the slot's next MMA group; the pool never waits for the copy.
+              const long long row0 = (blockIdx.x + (long long)i * gridDim.x) * kTcTileM;
+              if (a.B - row0 >= kTcTileM) {
+                ptx::bulk_s2g(a.obs_rw + row0 * a.in_dim, stage, tile_bytes);
+                ptx::bulk_wait_read();
+              }
+              if (i + 2 < n_local) load_tile(i + 2);
+            }
           }
           __syncwarp();
         } else {
@@ -483,6 +496,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
     uint32_t n_sat = 0u;                     // flag 8: (row, operand block) pairs with a saturated fp16 operand seen by this thread
     const bool masked = (a.flags & 5u) && a.button0 != nullptr;   // the clamp/mask and the kp selection read the button
     int b0_s0 = 0, b0_s1 = 0;                // dead-man buttons of this thread's row in the two slots' tiles
+    // fused step: the row's previous published action (column block 3) / last joystick command (column block 0) for the
+    // NEXT conversion job, requested in the output job that precedes it (global loads, ~1 us under load)
+    float4 pf_act[3] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+    float pf_vel[3] = {0.f, 0.f, 0.f};
+    auto prefetch_state = [&](int pair, int s) {          // for conv_job(pair, s)
+      const long long row = (blockIdx.x + (long long)(pair * 2 + s) * gridDim.x) * kTcTileM + m;
+      if (row < a.B) {
+        if (cb == 3) {
+          const float4* p4 = reinterpret_cast<const float4*>(a.act + row * kDof);
+#pragma unroll
+          for (int q = 0; q < 3; ++q) pf_act[q] = p4[q];
+        } else if (cb == 0) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) pf_vel[c] = a.vel_cmd[row * 3 + c];
+        }
+      }
+    };
     // ---- conv(s): fp32 observation rows -> 16-bit layer-0 A operand, constant ones at K = in_dim, in_dim+1.
     //      chunk c8 (16 K elements = 8 columns) lands at 32*(c8/2) + 8*(c8%2) of buffer phi: block cb = chunks 2cb, 2cb+1
     auto conv_job = [&](int pair, int s) {
@@ -506,14 +536,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
           tc_term_range(cb, a.H, lo, hi);
           if (!full) for (int k = lo; k < hi; ++k) srow[k] = a.obs_rw[(row0 + m) * a.in_dim + k];   // ragged tile: no bulk load
           const uint32_t* rw = full ? s_raw + m * kTcRawWords : reinterpret_cast<const uint32_t*>(a.raw + row0 + m);
-          tc_update_terms(a, cb, srow, rw, row0 + m, &s_button[(s * 2 + (pair & 1)) * kTcTileM + m]);
+          tc_update_terms(a, cb, srow, rw, row0 + m, &s_button[(s * 2 + (pair & 1)) * kTcTileM + m], pf_act, pf_vel);
           if (!full) for (int k = lo; k < hi; ++k) a.obs_rw[(row0 + m) * a.in_dim + k] = srow[k];
         }
-        ptx::fence_proxy_async_smem();
+        ptx::fence_proxy_async_smem();     // the control warp bulk-copies the stage to global memory once all warps signalled
         __syncwarp();
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");       // the quarter's four column blocks
-        if (full && cb == 0 && lane == 0)
-          ptx::bulk_s2g(a.obs_rw + (row0 + quarter * 32) * a.in_dim, srow, (uint32_t)(32 * a.in_dim * 4));
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");       // the quarter's four column blocks: the
+                                                                               // conversion below reads their columns
       }
       if ((valid == kTcTileM || kFused) && even) {
         // full tile in shared memory, rows 8-byte aligned: vector loads, uniform per-pair classification
@@ -543,7 +572,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
         tc_conv_slow<kFp16>(a, rowp, m < valid, 2 * cb, c8_hi, a0_t);
       }
       ptx::tc_wait_st();
-      if constexpr (kFused) { if (cb == 0 && lane == 0) ptx::bulk_wait_read(); }   // the stage may be refilled after this job
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&a_blk[s * kTcBlocks]);
@@ -610,7 +638,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
     // a whole job of cover each (they used to be waited for).  Hazards: conv'(s) writes the buffer that held A(L),
     // consumed by the MMA out(s) has just waited for; the layer-0 MMA of the new tile overwrites the buffer out(s)
     // reads, but it is issued only after ALL warps signalled conv'(s), i.e. after their out(s) reads.
-    for (int s = 0; s < min(2, n_local); ++s) conv_job(0, s);
+    for (int s = 0; s < min(2, n_local); ++s) {
+      if constexpr (kFused) prefetch_state(0, s);
+      conv_job(0, s);
+    }
     for (int pair = 0; pair * 2 < n_local; ++pair) {
       const int ns = min(2, n_local - pair * 2);
       const int ns_next = max(0, min(2, n_local - (pair + 1) * 2));
@@ -677,6 +708,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
       }
 
       for (int s = 0; s < ns; ++s) {
+        if constexpr (kFused) { if (s < ns_next) prefetch_state(pair + 1, s); }   // lands while the output job runs
         out_job(pair, s);
         // With an even number of hidden layers the output accumulator shares its TMEM buffer with the next tile's
         // layer-0 operand: the four warps of a lane quarter (the only ones touching these lanes) meet before any of
