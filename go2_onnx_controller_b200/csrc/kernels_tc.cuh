@@ -531,6 +531,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
         float* srow = reinterpret_cast<float*>(stage0 + s * stage_bytes) + (size_t)m * a.in_dim;
         const bool full = valid == kTcTileM;
         ptx::mbar_wait(raw_full, (uint32_t)(s & 1));       // CTA-local tile i = 2*pair + s: phase i & 1
+        TC_TRACE(0xA00u | (uint32_t)s);
         if (m < valid) {
           int lo, hi;
           tc_term_range(cb, a.H, lo, hi);
@@ -539,10 +540,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
           tc_update_terms(a, cb, srow, rw, row0 + m, &s_button[(s * 2 + (pair & 1)) * kTcTileM + m], pf_act, pf_vel);
           if (!full) for (int k = lo; k < hi; ++k) a.obs_rw[(row0 + m) * a.in_dim + k] = srow[k];
         }
+        TC_TRACE(0xB00u | (uint32_t)s);
         ptx::fence_proxy_async_smem();     // the control warp bulk-copies the stage to global memory once all warps signalled
         __syncwarp();
         asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");       // the quarter's four column blocks: the
                                                                                // conversion below reads their columns
+        TC_TRACE(0xC00u | (uint32_t)s);
       }
       if ((valid == kTcTileM || kFused) && even) {
         // full tile in shared memory, rows 8-byte aligned: vector loads, uniform per-pair classification

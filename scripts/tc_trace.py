@@ -23,16 +23,27 @@ if os.environ.get("GO2P_TIME_IN"):      # synthetic Go2-topology policy with ano
     onnx_writer.write_policy(model, ws, bs)
 pb = pkg.PolicyBatch(model)
 d_obs = torch.randn((B, width), device="cuda"); d_act = torch.empty((B, 12), device="cuda")
+FUSED = os.environ.get("GO2P_TRACE_STEP") == "1"      # trace the fused fleet step (go2p_step_batch) instead of the plain forward
+if FUSED:
+    import ctypes as C, bench
+    arr = bench.synthetic_raw_states(capi, 4096, seed=3)
+    raw_np = np.frombuffer(bytes(arr), np.uint8).reshape(4096, C.sizeof(capi.RawState))
+    d_raw = torch.from_numpy(np.tile(raw_np, (B // 4096, 1)).copy()).cuda()
+    d_obs = torch.zeros((B, 98), device="cuda"); d_vel = torch.zeros((B, 3), device="cuda")
+    d_act = torch.zeros((B, 12), device="cuda"); d_q = torch.zeros((B, 12), device="cuda", dtype=torch.float64)
 for _ in range(3):
     trace.zero_()
     torch.cuda.synchronize()
-    pb.infer_device(d_obs.data_ptr(), d_act.data_ptr(), B, capi.PREC_FP16)
+    if FUSED:
+        pb.step_device(d_raw.data_ptr(), d_vel.data_ptr(), d_obs.data_ptr(), d_act.data_ptr(), d_q.data_ptr(), B, capi.PREC_FP16)
+    else:
+        pb.infer_device(d_obs.data_ptr(), d_act.data_ptr(), B, capi.PREC_FP16)
     torch.cuda.synchronize()
 t = trace.cpu().numpy().reshape(34, 2048)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 np.save(os.path.join(ROOT, "gpurun_out", "tc_trace_raw.npy"), t)
 names = {1: "C tma issue", 2: "C a_ready", 3: "C committed", 4: "W conv acquired", 6: "W E acquired", 7: "W arrived", 8: "W out acquired",
-         9: "W out done", 10: "W A buffer free", 11: "W st drained", 12: "W next acquired", 15: "W fine"}
+         9: "W out done", 10: "W raw landed", 11: "W terms updated", 12: "W quarter met", 15: "W fine"}
 c0 = min(int(t[w, 1]) for w in range(17) if t[w, 2046] > 0)
 for w in warps:
     n = int(t[w, 2046]); ev = t[w, 0:2 * n:2]; ck = t[w, 1:2 * n:2]
