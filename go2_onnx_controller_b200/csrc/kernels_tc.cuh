@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(const __grid_cons
       if ((valid == kTcTileM || kFused) && even) {
         // full tile in shared memory, rows 8-byte aligned: vector loads, uniform per-pair classification
         const float2* r2 = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(stage0 + s * stage_bytes) + (size_t)m * a.in_dim);
-#pragma unroll 1
+#pragma unroll 2
         for (int c8 = 2 * cb; c8 < c8_hi; ++c8) {
           uint32_t q[8];
           if (c8 * 16 + 16 <= a.in_dim) {
