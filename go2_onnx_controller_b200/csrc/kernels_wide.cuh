@@ -430,9 +430,10 @@ inline int wide_prepare(const MlpModel& m, std::vector<void*>& dev_owned, WideMo
 
 // Launch mode of the GEMM kernels: 1 = one CTA per tile (default), 2 = cluster of two with TMA multicast of the weight
 // tile, 3 = CTA pair (tcgen05 cta_group::2, M256 tiles).  All three pass the same tests.  Measured on B200
-// (scripts/gpu_wide_variants.sh, 606,208 rows): 1: 2.25 ms, 2: 2.41 ms, 3: 3.19 ms.  ncu: mode 3 does cut the L2 -> SM
-// bytes by a third (233 -> 155 MB in layer 2) but its MMAs retire at a quarter of the single-CTA rate -- the
-// leader/peer hand-offs (full-barrier relay, multicast commits) sit in the per-chunk critical path; round-2 work.
+// (scripts/gpu_wide_variants.sh, 606,208 rows, round-1 pass size): 1: 2.25 ms, 2: 2.41 ms, 3: 3.19 ms.  ncu: mode 3
+// does cut the L2 -> SM bytes by a third (233 -> 155 MB in layer 2) but its MMAs retire at a quarter of the single-CTA
+// rate -- the leader/peer hand-offs (full-barrier relay, multicast commits) sit in the per-chunk critical path, and a
+// 1-D bulk copy cannot complete on the peer CTA's barrier.  Modes 2 and 3 are kept as measured build options.
 #ifndef GO2P_WD_CLUSTER
 #define GO2P_WD_CLUSTER 1
 #endif
